@@ -1,0 +1,901 @@
+// goetia_b200/csrc/capi.cu -- host side of the C ABI declared in include/goetia_b200.h.
+//
+// Owns all CUDA state: the storages' tables in HBM, a two-slot chunk pipeline (H2D copy of
+// chunk n+1 overlaps the kernels of chunk n on a second stream), and device-resident packed
+// batches.  No CPU fallback exists anywhere in this file: if CUDA is unusable every entry
+// point fails with an error.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/goetia_b200.h"
+#include "kernels.cuh"
+#include "sketch.cuh"
+
+using namespace gt;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return -1;
+}
+#define CU(call)                                                                            \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return -1;                                                                      \
+        }                                                                                   \
+    } while (0)
+#define CUP(call)                                                                           \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return nullptr;                                                                 \
+        }                                                                                   \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    // grow-only; caller guarantees the owning stream is idle w.r.t. this buffer when growing
+    int reserve(size_t n, cudaStream_t s) {
+        if (n <= cap) return 0;
+        if (p) {
+            CU(cudaStreamSynchronize(s));
+            CU(cudaFree(p));
+            p = nullptr;
+            cap = 0;
+        }
+        size_t want = n + n / 8 + 256;
+        CU(cudaMalloc(&p, want));
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    DevBuf ascii, words, offsets, flags, coarse, nmask, kcount, koff, partial, hits, out16, out64a, out64b, out8;
+};
+
+struct Context {
+    bool ready = false;
+    int device = -1;
+    int sms = 0;
+    cudaStream_t main = nullptr;
+    Slot slot[2];
+    unsigned long long* d_scratch = nullptr;  // [0] k-mer total, [1] occupied, [2..7] spare
+    unsigned long long* h_scratch = nullptr;  // pinned mirror
+};
+static Context g_ctx;
+static std::mutex g_mu;
+
+static int ensure_ctx() {
+    if (g_ctx.ready) return 0;
+    return fail("gt_init() has not been called");
+}
+
+// chunk size of the host-buffer pipeline (bases).  256 Mi bases = 256 MiB of ASCII per slot.
+static uint64_t chunk_bases() {
+    static uint64_t v = 0;
+    if (!v) {
+        const char* e = getenv("GT_CHUNK_BASES");
+        v = e ? strtoull(e, nullptr, 10) : (256ull << 20);
+        if (v < 1024) v = 1024;
+    }
+    return v;
+}
+
+extern "C" int gt_abi_version(void) { return GT_ABI_VERSION; }
+extern "C" const char* gt_last_error(void) { return g_err.c_str(); }
+
+extern "C" int gt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int gt_init(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ctx.ready) {
+        if (g_ctx.device == device) return 0;
+        return fail("gt_init: already initialised on device %d (one process drives one GPU)", g_ctx.device);
+    }
+    int n = 0;
+    CU(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail("gt_init: device %d out of range (%d visible)", device, n);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail("gt_init: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    g_ctx.sms = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&g_ctx.main, cudaStreamNonBlocking));
+    for (auto& s : g_ctx.slot) CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&g_ctx.d_scratch, 8 * sizeof(unsigned long long)));
+    CU(cudaMemset(g_ctx.d_scratch, 0, 8 * sizeof(unsigned long long)));
+    CU(cudaMallocHost(&g_ctx.h_scratch, 8 * sizeof(unsigned long long)));
+    g_ctx.device = device;
+    g_ctx.ready = true;
+    return 0;
+}
+
+extern "C" int gt_synchronize(void) {
+    if (ensure_ctx()) return -1;
+    CU(cudaSetDevice(g_ctx.device));
+    CU(cudaDeviceSynchronize());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// table sizing: get_n_primes_near_x, storage/storage.hh:146-190 (host only, one-off)
+// ------------------------------------------------------------------------------------------
+static bool is_prime_u64(uint64_t n) {
+    if (n < 2) return false;
+    if (n < 4) return true;
+    if (n % 2 == 0) return false;
+    for (uint64_t i = 3; i * i <= n; i += 2)
+        if (n % i == 0) return false;
+    return true;
+}
+extern "C" int gt_primes_near(uint32_t n, uint64_t x, uint64_t* out) {
+    if (!out) return fail("gt_primes_near: out is NULL");
+    if (x == 1) { out[0] = 1; return 1; }  // storage.hh:169-172
+    if (x == 0) return 0;
+    uint64_t i = x - 1;
+    if (i % 2 == 0) { if (i == 0) return 0; --i; }
+    uint32_t k = 0;
+    while (k != n) {
+        if (is_prime_u64(i)) out[k++] = i;
+        if (i == 1) break;
+        i -= 2;
+    }
+    return (int)k;
+}
+
+// ------------------------------------------------------------------------------------------
+// storage
+// ------------------------------------------------------------------------------------------
+struct gt_storage {
+    int kind = 0;
+    int n = 0;
+    uint64_t sizes[MAX_TABLES];
+    uint64_t ref_bytes[MAX_TABLES];    // bytes the reference allocates
+    uint64_t alloc_bytes[MAX_TABLES];  // bytes we allocate (multiple of 16, >= ref_bytes)
+    TableSet ts;
+    unsigned long long* d_n_unique = nullptr;
+};
+
+static uint64_t ref_table_bytes(int kind, uint64_t size) {
+    return kind == GT_STORAGE_BIT ? size / 8 + 1 : kind == GT_STORAGE_BYTE ? size : size / 2 + 1;
+}
+
+extern "C" gt_storage* gt_storage_create(int kind, const uint64_t* tablesizes, int n_tables) {
+    if (ensure_ctx()) return nullptr;
+    if (kind < 0 || kind > 2) { fail("gt_storage_create: unknown storage kind %d", kind); return nullptr; }
+    if (!tablesizes || n_tables < 1 || n_tables > MAX_TABLES) {
+        fail("gt_storage_create: n_tables must be 1..%d", MAX_TABLES);
+        return nullptr;
+    }
+    CUP(cudaSetDevice(g_ctx.device));
+    gt_storage* st = new gt_storage();
+    st->kind = kind;
+    st->n = n_tables;
+    memset(&st->ts, 0, sizeof st->ts);
+    st->ts.n = n_tables;
+    st->ts.kind = kind;
+    for (int i = 0; i < n_tables; ++i) {
+        uint64_t d = tablesizes[i];
+        if (d == 0 || d > (1ull << 63)) {
+            fail("gt_storage_create: table size %llu out of range", (unsigned long long)d);
+            gt_storage_destroy(st);
+            return nullptr;
+        }
+        st->sizes[i] = d;
+        st->ref_bytes[i] = ref_table_bytes(kind, d);
+        st->alloc_bytes[i] = (st->ref_bytes[i] + 15) / 16 * 16;
+        st->ts.size[i] = d;
+        st->ts.magic[i] = ~0ull / d;
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, st->alloc_bytes[i]);
+        if (e != cudaSuccess) {
+            fail("gt_storage_create: cudaMalloc(%llu) failed: %s", (unsigned long long)st->alloc_bytes[i], cudaGetErrorString(e));
+            gt_storage_destroy(st);
+            return nullptr;
+        }
+        st->ts.ptr[i] = static_cast<uint32_t*>(p);
+    }
+    if (cudaMalloc(&st->d_n_unique, sizeof(unsigned long long)) != cudaSuccess) {
+        fail("gt_storage_create: cudaMalloc(counter) failed");
+        gt_storage_destroy(st);
+        return nullptr;
+    }
+    if (gt_storage_reset(st) != 0) { gt_storage_destroy(st); return nullptr; }
+    return st;
+}
+
+extern "C" void gt_storage_destroy(gt_storage* st) {
+    if (!st) return;
+    cudaDeviceSynchronize();
+    for (int i = 0; i < st->n; ++i)
+        if (st->ts.ptr[i]) cudaFree(st->ts.ptr[i]);
+    if (st->d_n_unique) cudaFree(st->d_n_unique);
+    delete st;
+}
+
+extern "C" int gt_storage_reset(gt_storage* st) {
+    if (ensure_ctx()) return -1;
+    if (!st) return fail("gt_storage_reset: NULL storage");
+    for (int i = 0; i < st->n; ++i) CU(cudaMemsetAsync(st->ts.ptr[i], 0, st->alloc_bytes[i], g_ctx.main));
+    CU(cudaMemsetAsync(st->d_n_unique, 0, sizeof(unsigned long long), g_ctx.main));
+    CU(cudaStreamSynchronize(g_ctx.main));
+    return 0;
+}
+
+extern "C" int gt_storage_kind(const gt_storage* st) { return st ? st->kind : -1; }
+extern "C" int gt_storage_n_tables(const gt_storage* st) { return st ? st->n : -1; }
+extern "C" int gt_storage_tablesizes(const gt_storage* st, uint64_t* out) {
+    if (!st || !out) return fail("gt_storage_tablesizes: NULL argument");
+    for (int i = 0; i < st->n; ++i) out[i] = st->sizes[i];
+    return st->n;
+}
+extern "C" uint64_t gt_storage_table_bytes(const gt_storage* st, int i) {
+    if (!st || i < 0 || i >= st->n) return 0;
+    return st->ref_bytes[i];
+}
+extern "C" void* gt_storage_device_table(gt_storage* st, int i) {
+    if (!st || i < 0 || i >= st->n) return nullptr;
+    return st->ts.ptr[i];
+}
+
+extern "C" int gt_storage_download_table(gt_storage* st, int i, uint8_t* host_dst) {
+    if (ensure_ctx()) return -1;
+    if (!st || !host_dst || i < 0 || i >= st->n) return fail("gt_storage_download_table: bad argument");
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(host_dst, st->ts.ptr[i], st->ref_bytes[i], cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int gt_storage_upload_table(gt_storage* st, int i, const uint8_t* host_src) {
+    if (ensure_ctx()) return -1;
+    if (!st || !host_src || i < 0 || i >= st->n) return fail("gt_storage_upload_table: bad argument");
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemset(st->ts.ptr[i], 0, st->alloc_bytes[i]));
+    CU(cudaMemcpy(st->ts.ptr[i], host_src, st->ref_bytes[i], cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int grid_for(uint64_t items, int per_block, int blocks_per_sm) {
+    uint64_t want = (items + per_block - 1) / per_block;
+    uint64_t cap = (uint64_t)g_ctx.sms * blocks_per_sm;
+    if (want < 1) want = 1;
+    return (int)std::min(want, cap);
+}
+
+extern "C" int gt_storage_stats(gt_storage* st, uint64_t* n_unique, uint64_t* n_occupied) {
+    if (ensure_ctx()) return -1;
+    if (!st) return fail("gt_storage_stats: NULL storage");
+    CU(cudaDeviceSynchronize());
+    cudaStream_t s = g_ctx.main;
+    unsigned long long* d_occ = g_ctx.d_scratch + 1;
+    CU(cudaMemsetAsync(d_occ, 0, sizeof(unsigned long long), s));
+    // only the slots of the reference's table count; the padding words are always zero
+    uint64_t n_words = st->alloc_bytes[0] / 4;
+    int grid = grid_for(n_words, 256 * 8, 8);
+    if (st->kind == 0) k_count_occupied<0><<<grid, 256, 0, s>>>(st->ts.ptr[0], n_words, st->sizes[0], d_occ);
+    else if (st->kind == 1) k_count_occupied<1><<<grid, 256, 0, s>>>(st->ts.ptr[0], n_words, st->sizes[0], d_occ);
+    else k_count_occupied<2><<<grid, 256, 0, s>>>(st->ts.ptr[0], n_words, st->sizes[0], d_occ);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(g_ctx.h_scratch + 1, d_occ, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(g_ctx.h_scratch + 2, st->d_n_unique, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (n_occupied) *n_occupied = g_ctx.h_scratch[1];
+    if (n_unique) *n_unique = g_ctx.h_scratch[2];
+    return 0;
+}
+
+extern "C" int gt_storage_set_n_unique(gt_storage* st, uint64_t n_unique) {
+    if (ensure_ctx()) return -1;
+    if (!st) return fail("gt_storage_set_n_unique: NULL storage");
+    CU(cudaDeviceSynchronize());
+    unsigned long long v = n_unique;
+    CU(cudaMemcpy(st->d_n_unique, &v, sizeof v, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int gt_storage_update_from(gt_storage* dst, const gt_storage* src) {
+    if (ensure_ctx()) return -1;
+    if (!dst || !src) return fail("gt_storage_update_from: NULL storage");
+    if (dst->kind != GT_STORAGE_BIT || src->kind != GT_STORAGE_BIT)
+        return fail("gt_storage_update_from: only BitStorage can be unioned (bitstorage.cc:103-137)");
+    if (dst->n != src->n || memcmp(dst->sizes, src->sizes, sizeof(uint64_t) * dst->n) != 0)
+        return fail("both nodegraphs must have same table sizes");
+    CU(cudaDeviceSynchronize());
+    for (int i = 0; i < dst->n; ++i) {
+        uint64_t n_words = dst->alloc_bytes[i] / 4;
+        k_or_tables<<<grid_for(n_words, 256 * 4, 8), 256, 0, g_ctx.main>>>(dst->ts.ptr[i], src->ts.ptr[i], n_words);
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(g_ctx.main));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel dispatch
+// ------------------------------------------------------------------------------------------
+template <int OP, int KIND, bool CAN, bool TRACK, int NT>
+static int launch_walk_t(const WalkArgs& a, const TableSet& ts, cudaStream_t s) {
+    auto kern = k_walk<OP, KIND, CAN, TRACK, NT>;
+    static int occ = 0;
+    const int halo_words = ((a.K - 1 + 31) >> 5) + 1;
+    const size_t smem = (16 + TILE_THREADS + halo_words) * sizeof(uint64_t);
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!occ) {
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TILE_THREADS, smem));
+        if (occ < 1) occ = 1;
+    }
+    uint64_t n_tiles = (a.n_bases + TILE_POS - 1) / TILE_POS;
+    if (n_tiles == 0) return 0;
+    int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)g_ctx.sms * occ);
+    kern<<<grid, TILE_THREADS, smem, s>>>(a, ts);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <int OP, int KIND, bool CAN, bool TRACK>
+static int launch_walk_nt(const WalkArgs& a, const TableSet& ts, cudaStream_t s) {
+    if (ts.n == 4) return launch_walk_t<OP, KIND, CAN, TRACK, 4>(a, ts, s);
+    return launch_walk_t<OP, KIND, CAN, TRACK, 0>(a, ts, s);
+}
+template <int OP, int KIND, bool TRACK>
+static int launch_walk_can(int shifter, const WalkArgs& a, const TableSet& ts, cudaStream_t s) {
+    if (shifter == GT_SHIFTER_CAN) return launch_walk_nt<OP, KIND, true, TRACK>(a, ts, s);
+    return launch_walk_nt<OP, KIND, false, TRACK>(a, ts, s);
+}
+template <int OP, bool TRACK>
+static int launch_walk_kind(int shifter, const WalkArgs& a, const TableSet& ts, cudaStream_t s) {
+    switch (ts.kind) {
+        case 0: return launch_walk_can<OP, 0, TRACK>(shifter, a, ts, s);
+        case 1: return launch_walk_can<OP, 1, TRACK>(shifter, a, ts, s);
+        default: return launch_walk_can<OP, 2, TRACK>(shifter, a, ts, s);
+    }
+}
+static int launch_hash(int shifter, const WalkArgs& a, cudaStream_t s) {
+    TableSet ts;
+    memset(&ts, 0, sizeof ts);
+    if (shifter == GT_SHIFTER_CAN) return launch_walk_t<OP_HASH, 0, true, false, 0>(a, ts, s);
+    return launch_walk_t<OP_HASH, 0, false, false, 0>(a, ts, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// device-resident batch
+// ------------------------------------------------------------------------------------------
+struct gt_batch {
+    uint64_t n_reads = 0, n_bases = 0, n_words = 0, n_words_alloc = 0, base0 = 0;
+    uint64_t* d_words = nullptr;
+    uint64_t* d_offsets = nullptr;
+    uint8_t* d_flags = nullptr;
+    uint32_t* d_coarse = nullptr;
+    bool owns = false;
+    int cached_K = -1;
+    int64_t cached_kmers = 0;
+};
+
+static uint64_t halo_alloc_words() { return 2052; }  // covers K up to 65535 plus the +1 vector lane
+
+// pack ASCII already on the device (d_ascii, d_offsets are device pointers; offsets absolute,
+// base0 = value of offsets[0]) into b's buffers on stream s.
+static int pack_on_device(const uint8_t* d_ascii, const uint64_t* d_offsets, uint64_t n_reads, uint64_t n_bases,
+                          uint64_t base0, uint64_t* d_words, uint64_t n_words_alloc, uint8_t* d_flags,
+                          uint32_t* d_coarse, cudaStream_t s, uint32_t* d_nmask = nullptr) {
+    uint64_t n_words = (n_bases + 31) / 32;
+    CU(cudaMemsetAsync(d_flags, 0, n_reads ? n_reads : 1, s));
+    if (n_words_alloc > n_words) CU(cudaMemsetAsync(d_words + n_words, 0, (n_words_alloc - n_words) * 8, s));
+    if (d_nmask && n_words_alloc > n_words) CU(cudaMemsetAsync(d_nmask + n_words, 0, (n_words_alloc - n_words) * 4, s));
+    if (n_words) {
+        k_pack<<<grid_for(n_words, 256, 16), 256, 0, s>>>(d_ascii, n_bases, d_offsets, n_reads, base0, d_words, n_words, d_flags, d_nmask);
+        CU(cudaGetLastError());
+    }
+    if (n_reads) {
+        k_coarse<<<grid_for(n_reads, 256, 16), 256, 0, s>>>(d_offsets, n_reads, base0, d_coarse);
+        CU(cudaGetLastError());
+    }
+    return 0;
+}
+
+static WalkArgs make_args(const gt_batch& b, int K) {
+    WalkArgs a;
+    memset(&a, 0, sizeof a);
+    a.words = b.d_words;
+    a.n_words_alloc = b.n_words_alloc;
+    a.offsets = b.d_offsets;
+    a.flags = b.d_flags;
+    a.coarse = b.d_coarse;
+    a.base0 = b.base0;
+    a.n_reads = b.n_reads;
+    a.n_bases = b.n_bases;
+    a.K = K;
+    return a;
+}
+
+// Stage one chunk of host reads [r0, r1) into slot `sl` and pack it.  Fills `view`.
+static int stage_chunk(Slot& sl, const char* bases, const uint64_t* offsets, uint64_t r0, uint64_t r1, gt_batch& view,
+                       bool want_nmask = false) {
+    cudaStream_t s = sl.stream;
+    uint64_t base0 = offsets[r0], n_bases = offsets[r1] - base0, n_reads = r1 - r0;
+    uint64_t n_words = (n_bases + 31) / 32, n_words_alloc = n_words + halo_alloc_words();
+    if (sl.ascii.reserve(n_bases + 64, s)) return -1;
+    if (sl.words.reserve(n_words_alloc * 8, s)) return -1;
+    if (sl.offsets.reserve((n_reads + 1) * 8, s)) return -1;
+    if (sl.flags.reserve(n_reads + 1, s)) return -1;
+    if (sl.coarse.reserve(((n_bases >> COARSE_SHIFT) + 2) * 4, s)) return -1;
+    if (want_nmask && sl.nmask.reserve(n_words_alloc * 4, s)) return -1;
+    if (n_bases) CU(cudaMemcpyAsync(sl.ascii.p, bases + base0, n_bases, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(sl.offsets.p, offsets + r0, (n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
+    if (pack_on_device(sl.ascii.as<uint8_t>(), sl.offsets.as<uint64_t>(), n_reads, n_bases, base0, sl.words.as<uint64_t>(),
+                       n_words_alloc, sl.flags.as<uint8_t>(), sl.coarse.as<uint32_t>(), s,
+                       want_nmask ? sl.nmask.as<uint32_t>() : nullptr))
+        return -1;
+    view = gt_batch();
+    view.n_reads = n_reads;
+    view.n_bases = n_bases;
+    view.n_words = n_words;
+    view.n_words_alloc = n_words_alloc;
+    view.base0 = base0;
+    view.d_words = sl.words.as<uint64_t>();
+    view.d_offsets = sl.offsets.as<uint64_t>();
+    view.d_flags = sl.flags.as<uint8_t>();
+    view.d_coarse = sl.coarse.as<uint32_t>();
+    return 0;
+}
+
+static int check_reads(const char* who, const char* bases, const uint64_t* offsets, uint64_t n_reads, int K) {
+    if (ensure_ctx()) return -1;
+    if (K < 1 || K > 65535) return fail("%s: K=%d out of range (1..65535)", who, K);
+    if (n_reads && (!bases || !offsets)) return fail("%s: NULL bases/offsets", who);
+    if (n_reads >= (1ull << 32)) return fail("%s: more than 2^32-1 reads in one call", who);
+    return 0;
+}
+
+// split reads into chunks of <= chunk_bases() (always at least one read per chunk)
+static void chunk_ranges(const uint64_t* offsets, uint64_t n_reads, std::vector<uint64_t>& cuts) {
+    cuts.clear();
+    cuts.push_back(0);
+    uint64_t lim = chunk_bases();
+    uint64_t r = 0;
+    while (r < n_reads) {
+        uint64_t start = offsets[r];
+        // first read whose end exceeds start+lim
+        const uint64_t* it = std::upper_bound(offsets + r + 1, offsets + n_reads + 1, start + lim);
+        uint64_t r1 = (uint64_t)(it - offsets) - 1;
+        if (r1 <= r) r1 = r + 1;
+        cuts.push_back(r1);
+        r = r1;
+    }
+}
+
+static int validate_offsets(const char* who, const uint64_t* offsets, uint64_t n_reads) {
+    for (uint64_t r = 0; r < n_reads; ++r)
+        if (offsets[r + 1] < offsets[r]) return fail("%s: offsets must be non-decreasing (read %llu)", who, (unsigned long long)r);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// gt_batch (resident packed reads)
+// ------------------------------------------------------------------------------------------
+static gt_batch* batch_alloc(uint64_t n_reads, uint64_t n_bases) {
+    gt_batch* b = new gt_batch();
+    b->owns = true;
+    b->n_reads = n_reads;
+    b->n_bases = n_bases;
+    b->n_words = (n_bases + 31) / 32;
+    b->n_words_alloc = b->n_words + halo_alloc_words();
+    if (cudaMalloc(&b->d_words, b->n_words_alloc * 8) != cudaSuccess ||
+        cudaMalloc(&b->d_offsets, (n_reads + 1) * 8) != cudaSuccess ||
+        cudaMalloc(&b->d_flags, n_reads + 1) != cudaSuccess ||
+        cudaMalloc(&b->d_coarse, ((n_bases >> COARSE_SHIFT) + 2) * 4) != cudaSuccess) {
+        fail("gt_batch: out of device memory (%llu bases)", (unsigned long long)n_bases);
+        gt_batch_destroy(b);
+        return nullptr;
+    }
+    return b;
+}
+
+extern "C" void gt_batch_destroy(gt_batch* b) {
+    if (!b) return;
+    if (b->owns) {
+        cudaDeviceSynchronize();
+        if (b->d_words) cudaFree(b->d_words);
+        if (b->d_offsets) cudaFree(b->d_offsets);
+        if (b->d_flags) cudaFree(b->d_flags);
+        if (b->d_coarse) cudaFree(b->d_coarse);
+    }
+    delete b;
+}
+
+extern "C" gt_batch* gt_batch_pack_dev(const void* d_bases, const void* d_offsets, uint64_t n_reads, uint64_t n_bases) {
+    if (ensure_ctx()) return nullptr;
+    if (n_reads >= (1ull << 32)) { fail("gt_batch_pack_dev: too many reads"); return nullptr; }
+    gt_batch* b = batch_alloc(n_reads, n_bases);
+    if (!b) return nullptr;
+    cudaStream_t s = g_ctx.main;
+    // offsets of a device batch are required to start at 0
+    if (cudaMemcpyAsync(b->d_offsets, d_offsets, (n_reads + 1) * 8, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
+        pack_on_device(static_cast<const uint8_t*>(d_bases), b->d_offsets, n_reads, n_bases, 0, b->d_words, b->n_words_alloc,
+                       b->d_flags, b->d_coarse, s) != 0 ||
+        cudaStreamSynchronize(s) != cudaSuccess) {
+        if (g_err.empty()) fail("gt_batch_pack_dev: CUDA failure: %s", cudaGetErrorString(cudaGetLastError()));
+        gt_batch_destroy(b);
+        return nullptr;
+    }
+    return b;
+}
+
+extern "C" gt_batch* gt_batch_pack(const char* bases, const uint64_t* offsets, uint64_t n_reads) {
+    if (check_reads("gt_batch_pack", bases, offsets, n_reads, 1)) return nullptr;
+    if (validate_offsets("gt_batch_pack", offsets, n_reads)) return nullptr;
+    uint64_t base0 = n_reads ? offsets[0] : 0;
+    uint64_t n_bases = n_reads ? offsets[n_reads] - base0 : 0;
+    gt_batch* b = batch_alloc(n_reads, n_bases);
+    if (!b) return nullptr;
+    // stage the ASCII through the pipeline slots in chunks, packing straight into the batch
+    std::vector<uint64_t> rebased(n_reads + 1);
+    for (uint64_t r = 0; r <= n_reads; ++r) rebased[r] = offsets[r] - base0;
+    bool ok = cudaMemcpy(b->d_offsets, rebased.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemset(b->d_flags, 0, n_reads + 1) == cudaSuccess;
+    ok = ok && cudaMemset(b->d_words + b->n_words, 0, (b->n_words_alloc - b->n_words) * 8) == cudaSuccess;
+    // chunk on 32-base boundaries so each chunk fills whole words
+    uint64_t lim = chunk_bases() & ~31ull;
+    int which = 0;
+    for (uint64_t p = 0; ok && p < n_bases; p += lim, which ^= 1) {
+        Slot& sl = g_ctx.slot[which];
+        uint64_t nb = std::min(lim, n_bases - p);
+        if (sl.ascii.reserve(nb + 64, sl.stream)) { ok = false; break; }
+        ok = ok && cudaMemcpyAsync(sl.ascii.p, bases + base0 + p, nb, cudaMemcpyHostToDevice, sl.stream) == cudaSuccess;
+        uint64_t nw = (nb + 31) / 32;
+        k_pack<<<grid_for(nw, 256, 16), 256, 0, sl.stream>>>(sl.ascii.as<uint8_t>(), nb, b->d_offsets, n_reads, p,
+                                                             b->d_words + p / 32, nw, b->d_flags, nullptr);
+        ok = ok && cudaGetLastError() == cudaSuccess;
+    }
+    if (ok && n_reads) {
+        k_coarse<<<grid_for(n_reads, 256, 16), 256, 0, g_ctx.main>>>(b->d_offsets, n_reads, 0, b->d_coarse);
+        ok = cudaGetLastError() == cudaSuccess;
+    }
+    ok = ok && cudaDeviceSynchronize() == cudaSuccess;
+    if (!ok) {
+        if (g_err.empty()) fail("gt_batch_pack: CUDA failure: %s", cudaGetErrorString(cudaGetLastError()));
+        gt_batch_destroy(b);
+        return nullptr;
+    }
+    return b;
+}
+
+extern "C" uint64_t gt_batch_n_reads(const gt_batch* b) { return b ? b->n_reads : 0; }
+extern "C" uint64_t gt_batch_n_bases(const gt_batch* b) { return b ? b->n_bases : 0; }
+
+// k-mer total (+ optional per-read counts/status) of a batch on stream s; synchronises s.
+static int64_t batch_kmers(const gt_batch& b, int K, uint64_t* d_kcount, uint8_t* d_status, cudaStream_t s) {
+    unsigned long long* d_tot = g_ctx.d_scratch;
+    CU(cudaMemsetAsync(d_tot, 0, sizeof(unsigned long long), s));
+    if (b.n_reads) {
+        k_kmer_counts<<<grid_for(b.n_reads, 256, 16), 256, 0, s>>>(b.d_offsets, b.n_reads, K, b.d_flags, d_kcount, d_status, d_tot);
+        CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(g_ctx.h_scratch, d_tot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return (int64_t)g_ctx.h_scratch[0];
+}
+
+extern "C" int64_t gt_batch_n_kmers(gt_batch* b, int K) {
+    if (ensure_ctx()) return -1;
+    if (!b) return fail("gt_batch_n_kmers: NULL batch");
+    if (b->cached_K == K) return b->cached_kmers;
+    int64_t n = batch_kmers(*b, K, nullptr, nullptr, g_ctx.main);
+    if (n >= 0) { b->cached_K = K; b->cached_kmers = n; }
+    return n;
+}
+
+extern "C" int gt_batch_status(gt_batch* b, int K, uint8_t* status) {
+    if (ensure_ctx()) return -1;
+    if (!b || !status) return fail("gt_batch_status: NULL argument");
+    if (b->n_reads == 0) return 0;
+    Slot& sl = g_ctx.slot[0];
+    if (sl.out8.reserve(b->n_reads, sl.stream)) return -1;
+    if (batch_kmers(*b, K, nullptr, sl.out8.as<uint8_t>(), sl.stream) < 0) return -1;
+    CU(cudaMemcpy(status, sl.out8.p, b->n_reads, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+static int check_mode(const char* who, int mode) {
+    if (mode != GT_MODE_BLIND && mode != GT_MODE_FAST && mode != GT_MODE_EXACT) return fail("%s: unknown mode %d", who, mode);
+    if (mode == GT_MODE_EXACT) return fail("%s: GT_MODE_EXACT is not available in this build", who);
+    return 0;
+}
+
+static int launch_insert(gt_storage* st, int shifter, const gt_batch& b, int K, int mode, uint64_t* d_n_new, cudaStream_t s) {
+    WalkArgs a = make_args(b, K);
+    a.n_unique = st->d_n_unique;
+    a.n_new = d_n_new;
+    if (mode == GT_MODE_BLIND) return launch_walk_kind<OP_INSERT, false>(shifter, a, st->ts, s);
+    return launch_walk_kind<OP_INSERT, true>(shifter, a, st->ts, s);
+}
+
+extern "C" int64_t gt_insert_batch(gt_storage* st, int shifter, int K, gt_batch* b, int mode, void* stream) {
+    if (ensure_ctx()) return -1;
+    if (!st || !b) return fail("gt_insert_batch: NULL argument");
+    if (K < 1 || K > 65535) return fail("gt_insert_batch: K=%d out of range", K);
+    if (check_mode("gt_insert_batch", mode)) return -1;
+    int64_t n = gt_batch_n_kmers(b, K);
+    if (n < 0) return -1;
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : g_ctx.main;
+    if (launch_insert(st, shifter, *b, K, mode, nullptr, s)) return -1;
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer batch members
+// ------------------------------------------------------------------------------------------
+extern "C" int64_t gt_insert_sequences(gt_storage* st, int shifter, int K, const char* bases, const uint64_t* offsets,
+                                        uint64_t n_reads, int mode, uint64_t* n_new_per_read, uint8_t* status) {
+    if (check_reads("gt_insert_sequences", bases, offsets, n_reads, K)) return -1;
+    if (!st) return fail("gt_insert_sequences: NULL storage");
+    if (check_mode("gt_insert_sequences", mode)) return -1;
+    if (n_new_per_read && mode == GT_MODE_BLIND) return fail("gt_insert_sequences: n_new_per_read needs GT_MODE_FAST or GT_MODE_EXACT");
+    if (validate_offsets("gt_insert_sequences", offsets, n_reads)) return -1;
+    if (n_reads == 0) return 0;
+    CU(cudaSetDevice(g_ctx.device));
+    std::vector<uint64_t> cuts;
+    chunk_ranges(offsets, n_reads, cuts);
+    // k-mer total accumulates on the device across chunks (scratch[3]); read once at the end
+    unsigned long long* d_tot = g_ctx.d_scratch + 3;
+    CU(cudaMemsetAsync(d_tot, 0, sizeof(unsigned long long), g_ctx.slot[0].stream));
+    CU(cudaStreamSynchronize(g_ctx.slot[0].stream));
+    for (size_t c = 0; c + 1 < cuts.size(); ++c) {
+        Slot& sl = g_ctx.slot[c & 1];
+        cudaStream_t s = sl.stream;
+        uint64_t r0 = cuts[c], r1 = cuts[c + 1], nr = r1 - r0;
+        gt_batch view;
+        if (stage_chunk(sl, bases, offsets, r0, r1, view)) return -1;
+        uint8_t* d_status = nullptr;
+        if (status) {
+            if (sl.out8.reserve(nr, s)) return -1;
+            d_status = sl.out8.as<uint8_t>();
+        }
+        k_kmer_counts<<<grid_for(nr, 256, 16), 256, 0, s>>>(view.d_offsets, nr, K, view.d_flags, nullptr, d_status, d_tot);
+        CU(cudaGetLastError());
+        uint64_t* d_n_new = nullptr;
+        if (n_new_per_read) {
+            if (sl.out64a.reserve(nr * 8, s)) return -1;
+            d_n_new = sl.out64a.as<uint64_t>();
+            CU(cudaMemsetAsync(d_n_new, 0, nr * 8, s));
+        }
+        if (launch_insert(st, shifter, view, K, mode, d_n_new, s)) return -1;
+        if (status) CU(cudaMemcpyAsync(status + r0, d_status, nr, cudaMemcpyDeviceToHost, s));
+        if (n_new_per_read) CU(cudaMemcpyAsync(n_new_per_read + r0, d_n_new, nr * 8, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(g_ctx.slot[0].stream));
+    CU(cudaStreamSynchronize(g_ctx.slot[1].stream));
+    CU(cudaMemcpy(g_ctx.h_scratch + 3, d_tot, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return (int64_t)g_ctx.h_scratch[3];
+}
+
+// exclusive scan of per-read k-mer counts on stream s
+static int scan_counts(Slot& sl, const uint64_t* d_in, uint64_t n, uint64_t* d_out, cudaStream_t s) {
+    if (n == 0) return 0;
+    uint64_t per = (uint64_t)SCAN_BLOCK * SCAN_ITEMS;
+    uint64_t nb = (n + per - 1) / per;
+    if (sl.partial.reserve(nb * 8, s)) return -1;
+    k_scan_partials<<<(unsigned)nb, SCAN_BLOCK, 0, s>>>(d_in, n, sl.partial.as<uint64_t>());
+    k_scan_top<<<1, 1024, 0, s>>>(sl.partial.as<uint64_t>(), nb);
+    k_scan_final<<<(unsigned)nb, SCAN_BLOCK, 0, s>>>(d_in, n, sl.partial.as<uint64_t>(), d_out);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// Shared driver for the per-k-mer output paths (query counts / hashes).
+//   what: 0 = query -> counts(int16), 1 = hash -> fw/rc
+static int64_t per_kmer_outputs(int what, gt_storage* st, int shifter, int K, const char* bases, const uint64_t* offsets,
+                                uint64_t n_reads, int16_t* counts, uint64_t* fw, uint64_t* rc, uint8_t* status) {
+    std::vector<uint64_t> cuts;
+    chunk_ranges(offsets, n_reads, cuts);
+    int64_t total = 0;
+    for (size_t c = 0; c + 1 < cuts.size(); ++c) {
+        Slot& sl = g_ctx.slot[c & 1];
+        cudaStream_t s = sl.stream;
+        uint64_t r0 = cuts[c], r1 = cuts[c + 1], nr = r1 - r0;
+        gt_batch view;
+        if (stage_chunk(sl, bases, offsets, r0, r1, view)) return -1;
+        if (sl.kcount.reserve(nr * 8, s) || sl.koff.reserve(nr * 8, s) || sl.out8.reserve(nr, s)) return -1;
+        int64_t nk = batch_kmers(view, K, sl.kcount.as<uint64_t>(), sl.out8.as<uint8_t>(), s);
+        if (nk < 0) return -1;
+        if (scan_counts(sl, sl.kcount.as<uint64_t>(), nr, sl.koff.as<uint64_t>(), s)) return -1;
+        WalkArgs a = make_args(view, K);
+        a.koff = sl.koff.as<uint64_t>();
+        if (what == 0) {
+            if (sl.out16.reserve((uint64_t)nk * 2 + 2, s)) return -1;
+            a.counts = sl.out16.as<int16_t>();
+            if (launch_walk_kind<OP_QUERY, false>(shifter, a, st->ts, s)) return -1;
+            if (nk) CU(cudaMemcpyAsync(counts + total, a.counts, (uint64_t)nk * 2, cudaMemcpyDeviceToHost, s));
+        } else {
+            if (sl.out64a.reserve((uint64_t)nk * 8 + 8, s)) return -1;
+            a.fw = sl.out64a.as<uint64_t>();
+            if (shifter == GT_SHIFTER_CAN) {
+                if (sl.out64b.reserve((uint64_t)nk * 8 + 8, s)) return -1;
+                a.rc = sl.out64b.as<uint64_t>();
+            }
+            if (launch_hash(shifter, a, s)) return -1;
+            if (nk) {
+                CU(cudaMemcpyAsync(fw + total, a.fw, (uint64_t)nk * 8, cudaMemcpyDeviceToHost, s));
+                if (shifter == GT_SHIFTER_CAN && rc) CU(cudaMemcpyAsync(rc + total, a.rc, (uint64_t)nk * 8, cudaMemcpyDeviceToHost, s));
+            }
+        }
+        if (status) CU(cudaMemcpyAsync(status + r0, sl.out8.p, nr, cudaMemcpyDeviceToHost, s));
+        total += nk;
+    }
+    CU(cudaStreamSynchronize(g_ctx.slot[0].stream));
+    CU(cudaStreamSynchronize(g_ctx.slot[1].stream));
+    return total;
+}
+
+extern "C" int64_t gt_query_sequences(gt_storage* st, int shifter, int K, const char* bases, const uint64_t* offsets,
+                                       uint64_t n_reads, int16_t* counts, uint8_t* status) {
+    if (check_reads("gt_query_sequences", bases, offsets, n_reads, K)) return -1;
+    if (!st || !counts) return fail("gt_query_sequences: NULL argument");
+    if (validate_offsets("gt_query_sequences", offsets, n_reads)) return -1;
+    if (n_reads == 0) return 0;
+    CU(cudaSetDevice(g_ctx.device));
+    return per_kmer_outputs(0, st, shifter, K, bases, offsets, n_reads, counts, nullptr, nullptr, status);
+}
+
+extern "C" int64_t gt_hash_sequences(int shifter, int K, const char* bases, const uint64_t* offsets, uint64_t n_reads,
+                                      uint64_t* fw, uint64_t* rc, uint8_t* status) {
+    if (check_reads("gt_hash_sequences", bases, offsets, n_reads, K)) return -1;
+    if (!fw) return fail("gt_hash_sequences: fw is NULL");
+    if (validate_offsets("gt_hash_sequences", offsets, n_reads)) return -1;
+    if (n_reads == 0) return 0;
+    CU(cudaSetDevice(g_ctx.device));
+    return per_kmer_outputs(1, nullptr, shifter, K, bases, offsets, n_reads, nullptr, fw, rc, status);
+}
+
+extern "C" int64_t gt_median_count_at_least(gt_storage* st, int shifter, int K, const char* bases, const uint64_t* offsets,
+                                             uint64_t n_reads, uint32_t cutoff, uint8_t* pass, uint8_t* status) {
+    if (check_reads("gt_median_count_at_least", bases, offsets, n_reads, K)) return -1;
+    if (!st || !pass) return fail("gt_median_count_at_least: NULL argument");
+    if (validate_offsets("gt_median_count_at_least", offsets, n_reads)) return -1;
+    if (n_reads == 0) return 0;
+    CU(cudaSetDevice(g_ctx.device));
+    std::vector<uint64_t> cuts;
+    chunk_ranges(offsets, n_reads, cuts);
+    unsigned long long* d_tot = g_ctx.d_scratch + 3;
+    CU(cudaMemsetAsync(d_tot, 0, sizeof(unsigned long long), g_ctx.slot[0].stream));
+    CU(cudaStreamSynchronize(g_ctx.slot[0].stream));
+    for (size_t c = 0; c + 1 < cuts.size(); ++c) {
+        Slot& sl = g_ctx.slot[c & 1];
+        cudaStream_t s = sl.stream;
+        uint64_t r0 = cuts[c], r1 = cuts[c + 1], nr = r1 - r0;
+        gt_batch view;
+        if (stage_chunk(sl, bases, offsets, r0, r1, view)) return -1;
+        if (sl.kcount.reserve(nr * 8, s) || sl.hits.reserve(nr * 4, s) || sl.out8.reserve(2 * nr, s)) return -1;
+        uint8_t* d_status = sl.out8.as<uint8_t>();
+        uint8_t* d_pass = d_status + nr;
+        k_kmer_counts<<<grid_for(nr, 256, 16), 256, 0, s>>>(view.d_offsets, nr, K, view.d_flags, sl.kcount.as<uint64_t>(), d_status, d_tot);
+        CU(cudaGetLastError());
+        CU(cudaMemsetAsync(sl.hits.p, 0, nr * 4, s));
+        WalkArgs a = make_args(view, K);
+        a.hits = sl.hits.as<uint32_t>();
+        a.cutoff = cutoff;
+        if (launch_walk_kind<OP_MEDIAN, false>(shifter, a, st->ts, s)) return -1;
+        k_median_decide<<<grid_for(nr, 256, 16), 256, 0, s>>>(sl.kcount.as<uint64_t>(), a.hits, nr, d_pass);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(pass + r0, d_pass, nr, cudaMemcpyDeviceToHost, s));
+        if (status) CU(cudaMemcpyAsync(status + r0, d_status, nr, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(g_ctx.slot[0].stream));
+    CU(cudaStreamSynchronize(g_ctx.slot[1].stream));
+    CU(cudaMemcpy(g_ctx.h_scratch + 3, d_tot, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return (int64_t)g_ctx.h_scratch[3];
+}
+
+// ------------------------------------------------------------------------------------------
+// hash-vector members
+// ------------------------------------------------------------------------------------------
+template <int KIND, bool TRACK>
+static void launch_insert_hashes_t(const gt_storage* st, const uint64_t* d_h, uint64_t n, uint8_t* d_new, cudaStream_t s) {
+    int grid = grid_for(n, 256 * 4, 8);
+    if (st->n == 4) k_insert_hashes<KIND, TRACK, 4><<<grid, 256, 0, s>>>(d_h, n, st->ts, d_new, st->d_n_unique);
+    else k_insert_hashes<KIND, TRACK, 0><<<grid, 256, 0, s>>>(d_h, n, st->ts, d_new, st->d_n_unique);
+}
+
+extern "C" int gt_insert_hashes(gt_storage* st, const uint64_t* hashes, uint64_t n, int mode, uint8_t* is_new) {
+    if (ensure_ctx()) return -1;
+    if (!st || (n && !hashes)) return fail("gt_insert_hashes: NULL argument");
+    if (check_mode("gt_insert_hashes", mode)) return -1;
+    if (is_new && mode == GT_MODE_BLIND) return fail("gt_insert_hashes: is_new needs GT_MODE_FAST or GT_MODE_EXACT");
+    if (n == 0) return 0;
+    CU(cudaSetDevice(g_ctx.device));
+    const uint64_t chunk = 64ull << 20;  // hashes per chunk
+    for (uint64_t i0 = 0, c = 0; i0 < n; i0 += chunk, ++c) {
+        Slot& sl = g_ctx.slot[c & 1];
+        cudaStream_t s = sl.stream;
+        uint64_t m = std::min(chunk, n - i0);
+        if (sl.out64a.reserve(m * 8, s) || sl.out8.reserve(m, s)) return -1;
+        CU(cudaMemcpyAsync(sl.out64a.p, hashes + i0, m * 8, cudaMemcpyHostToDevice, s));
+        uint8_t* d_new = is_new ? sl.out8.as<uint8_t>() : nullptr;
+        const uint64_t* d_h = sl.out64a.as<uint64_t>();
+        bool track = mode != GT_MODE_BLIND;
+        switch (st->kind * 2 + (track ? 1 : 0)) {
+            case 0: launch_insert_hashes_t<0, false>(st, d_h, m, d_new, s); break;
+            case 1: launch_insert_hashes_t<0, true>(st, d_h, m, d_new, s); break;
+            case 2: launch_insert_hashes_t<1, false>(st, d_h, m, d_new, s); break;
+            case 3: launch_insert_hashes_t<1, true>(st, d_h, m, d_new, s); break;
+            case 4: launch_insert_hashes_t<2, false>(st, d_h, m, d_new, s); break;
+            default: launch_insert_hashes_t<2, true>(st, d_h, m, d_new, s); break;
+        }
+        CU(cudaGetLastError());
+        if (is_new) CU(cudaMemcpyAsync(is_new + i0, d_new, m, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(g_ctx.slot[0].stream));
+    CU(cudaStreamSynchronize(g_ctx.slot[1].stream));
+    return 0;
+}
+
+extern "C" int gt_query_hashes(gt_storage* st, const uint64_t* hashes, uint64_t n, int16_t* counts) {
+    if (ensure_ctx()) return -1;
+    if (!st || (n && (!hashes || !counts))) return fail("gt_query_hashes: NULL argument");
+    if (n == 0) return 0;
+    CU(cudaSetDevice(g_ctx.device));
+    const uint64_t chunk = 64ull << 20;
+    for (uint64_t i0 = 0, c = 0; i0 < n; i0 += chunk, ++c) {
+        Slot& sl = g_ctx.slot[c & 1];
+        cudaStream_t s = sl.stream;
+        uint64_t m = std::min(chunk, n - i0);
+        if (sl.out64a.reserve(m * 8, s) || sl.out16.reserve(m * 2, s)) return -1;
+        CU(cudaMemcpyAsync(sl.out64a.p, hashes + i0, m * 8, cudaMemcpyHostToDevice, s));
+        const uint64_t* d_h = sl.out64a.as<uint64_t>();
+        int16_t* d_c = sl.out16.as<int16_t>();
+        int grid = grid_for(m, 256 * 4, 8);
+        if (st->n == 4) {
+            if (st->kind == 0) k_query_hashes<0, 4><<<grid, 256, 0, s>>>(d_h, m, st->ts, d_c);
+            else if (st->kind == 1) k_query_hashes<1, 4><<<grid, 256, 0, s>>>(d_h, m, st->ts, d_c);
+            else k_query_hashes<2, 4><<<grid, 256, 0, s>>>(d_h, m, st->ts, d_c);
+        } else {
+            if (st->kind == 0) k_query_hashes<0, 0><<<grid, 256, 0, s>>>(d_h, m, st->ts, d_c);
+            else if (st->kind == 1) k_query_hashes<1, 0><<<grid, 256, 0, s>>>(d_h, m, st->ts, d_c);
+            else k_query_hashes<2, 0><<<grid, 256, 0, s>>>(d_h, m, st->ts, d_c);
+        }
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(counts + i0, d_c, m * 2, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(g_ctx.slot[0].stream));
+    CU(cudaStreamSynchronize(g_ctx.slot[1].stream));
+    return 0;
+}
+
+#include "sketch_host.inc"

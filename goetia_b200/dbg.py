@@ -1,0 +1,211 @@
+"""dBG<StorageType, ShifterType> mirror (include/goetia/dbg.hh:39-438) over the GPU backend.
+
+``dBG[BitStorage, CanLemireShifter].build(storage, hasher)`` reads like the cppyy surface
+(goetia/dbg.py:43-44, tests/utils.py:88-93).  Sequence members run the fused hash+insert /
+hash+query kernels; the batch members (``insert_sequences`` / ``query_sequences`` /
+``median_count_at_least``) take whole read batches and are the path the processors use.
+"""
+import numpy as np
+
+from . import _capi
+from .hashing import Canonical, Hash, InvalidSequenceException
+from .storage import _hash_value
+
+MODE_BLIND, MODE_FAST, MODE_EXACT = _capi.MODE_BLIND, _capi.MODE_FAST, _capi.MODE_EXACT
+
+
+class SequenceLengthException(InvalidSequenceException):
+    """kmeriterator.hh:57-59"""
+
+
+class InvalidCharacterException(ValueError):
+    """sequences/exceptions.hh:16-36"""
+
+
+class dBG:
+    storage_type = None
+    shifter_type = None
+    _specialisations = {}
+
+    def __class_getitem__(cls, params):
+        storage_t, shifter_t = params
+        key = (storage_t, shifter_t)
+        if key not in cls._specialisations:
+            name = "dBG<%s,%s>" % (storage_t.NAME, shifter_t.NAME)
+            cls._specialisations[key] = type(name, (dBG,), {"storage_type": storage_t, "shifter_type": shifter_t})
+        return cls._specialisations[key]
+
+    def __init__(self, storage, hasher_or_K, mode=MODE_FAST):
+        self.S = storage
+        if isinstance(hasher_or_K, int):
+            if self.shifter_type is None:
+                raise TypeError("use dBG[Storage, Shifter].build(storage, K)")
+            self.hasher = self.shifter_type(hasher_or_K)
+        else:
+            self.hasher = type(hasher_or_K)(hasher_or_K.K)
+        if self.storage_type is None:
+            self.storage_type = type(storage)
+        if self.shifter_type is None:
+            self.shifter_type = type(self.hasher)
+        self.K = self.hasher.K
+        self.mode = mode
+        self.hash_type = self.shifter_type.hash_type
+
+    @classmethod
+    def build(cls, storage, hasher_or_K, *args):
+        return cls(storage, hasher_or_K)
+
+    # -- clones (dbg.hh:97-101, :128-131) ------------------------------------------------------
+    def clone(self):
+        return type(self)(self.S.clone(), self.hasher, self.mode)
+
+    shallow_clone = clone  # pythonize_dbg.py:21-22
+
+    def reference_copy(self):
+        return type(self)(self.S, self.hasher, self.mode)
+
+    # -- shifter side ------------------------------------------------------------------------
+    def hash(self, kmer):
+        return self.hasher.hash(kmer)
+
+    def hashes(self, sequence):
+        return iter(self.hasher.hashes(sequence))
+
+    def get_hash_iter(self, sequence):
+        return iter(self.hasher.hashes(sequence))
+
+    def get_hasher(self):
+        return type(self.hasher)(self.K)
+
+    def _value(self, item):
+        if isinstance(item, (str, bytes)):
+            return self.hash(item).value()
+        return _hash_value(item)
+
+    # -- single k-mer members (dbg.hh:140-177) -------------------------------------------------
+    def insert(self, kmer):
+        return self.S.insert(self._value(kmer))
+
+    def insert_and_query(self, kmer):
+        return self.S.insert_and_query(self._value(kmer))
+
+    def query(self, kmer):
+        return self.S.query(self._value(kmer))
+
+    get = query  # pythonize_dbg.py:53
+
+    def add(self, item):
+        """pythonize_dbg.py:8-14"""
+        if not isinstance(item, int) and not isinstance(item, (Hash, Canonical)) and len(item) < self.K:
+            raise ValueError()
+        if isinstance(item, (int, Hash, Canonical)) or len(item) == self.K:
+            return self.insert(item)
+        return self.insert_sequence(item)
+
+    # -- stats ---------------------------------------------------------------------------------
+    def n_unique(self):
+        return self.S.n_unique_kmers()
+
+    def n_occupied(self):
+        return self.S.n_occupied()
+
+    def estimated_fp(self):
+        return self.S.estimated_fp()
+
+    def get_raw(self):
+        return self.S.get_raw_tables()
+
+    def suffix(self, kmer):
+        return kmer[len(kmer) - self.K + 1:]
+
+    def prefix(self, kmer):
+        return kmer[:self.K - 1]
+
+    def save(self, filename):
+        self.S.save(filename, self.K)
+
+    def load(self, filename):
+        self.S.load(filename)
+
+    def reset(self):
+        self.S.reset()
+
+    # -- batch members (the GPU hot path) --------------------------------------------------------
+    def insert_sequences(self, bases, offsets, mode=None, want_n_new=False, want_status=False):
+        """dBG::insert_sequence over a read batch.  Returns k-mers consumed (+ n_new, status)."""
+        L = _capi.lib()
+        bases, offsets = _capi.as_reads(bases, offsets)
+        n = offsets.size - 1
+        mode = self.mode if mode is None else mode
+        n_new = np.zeros(max(n, 1), dtype=np.uint64) if want_n_new else None
+        status = np.zeros(max(n, 1), dtype=np.uint8) if want_status else None
+        tot = _capi.check(L.gt_insert_sequences(self.S.handle, self.hasher.shifter_kind, self.K, bases.ctypes.data,
+                                                offsets.ctypes.data, n, mode,
+                                                n_new.ctypes.data if want_n_new else None,
+                                                status.ctypes.data if want_status else None), "gt_insert_sequences")
+        out = [int(tot)]
+        if want_n_new:
+            out.append(n_new[:n])
+        if want_status:
+            out.append(status[:n])
+        return out[0] if len(out) == 1 else tuple(out)
+
+    def query_sequences(self, bases, offsets, want_status=False):
+        """dBG::query_sequence over a read batch: counts of all k-mers, reads back to back."""
+        L = _capi.lib()
+        bases, offsets = _capi.as_reads(bases, offsets)
+        n = offsets.size - 1
+        lens = (offsets[1:] - offsets[:-1]).astype(np.int64)
+        cap = int(np.maximum(lens - self.K + 1, 0).sum())
+        counts = np.zeros(max(cap, 1), dtype=np.int16)
+        status = np.zeros(max(n, 1), dtype=np.uint8)
+        tot = _capi.check(L.gt_query_sequences(self.S.handle, self.hasher.shifter_kind, self.K, bases.ctypes.data,
+                                               offsets.ctypes.data, n, counts.ctypes.data, status.ctypes.data),
+                          "gt_query_sequences")
+        return (counts[:tot], status[:n]) if want_status else counts[:tot]
+
+    def median_count_at_least(self, bases, offsets, cutoff):
+        """DiginormFilter::median_count_at_least per read (diginorm.hh:35-68) -> uint8[n_reads]."""
+        L = _capi.lib()
+        bases, offsets = _capi.as_reads(bases, offsets)
+        n = offsets.size - 1
+        out = np.zeros(max(n, 1), dtype=np.uint8)
+        _capi.check(L.gt_median_count_at_least(self.S.handle, self.hasher.shifter_kind, self.K, bases.ctypes.data,
+                                               offsets.ctypes.data, n, int(cutoff), out.ctypes.data, None),
+                    "gt_median_count_at_least")
+        return out[:n]
+
+    # -- sequence members (dbg.hh:249-394) ---------------------------------------------------------
+    def _one(self, sequence):
+        if isinstance(sequence, bytes):
+            sequence = sequence.decode("ascii")
+        if len(sequence) < self.K:
+            raise SequenceLengthException("Sequence must have length >= K")
+        return _capi.reads_from_strings([sequence])
+
+    def insert_sequence(self, sequence, want_n_new=False):
+        """Returns len-K+1 (dbg.hh:296-305); with want_n_new also the new-k-mer count (:307-318)."""
+        bases, offsets = self._one(sequence)
+        if want_n_new:
+            tot, n_new, status = self.insert_sequences(bases, offsets, want_n_new=True, want_status=True)
+        else:
+            tot, status = self.insert_sequences(bases, offsets, want_status=True)
+        if status[0] & _capi.READ_INVALID:
+            raise InvalidCharacterException("sequence holds a non-ACGT character")
+        return (tot, int(n_new[0])) if want_n_new else tot
+
+    def query_sequence(self, sequence):
+        bases, offsets = self._one(sequence)
+        counts, status = self.query_sequences(bases, offsets, want_status=True)
+        if status[0] & _capi.READ_INVALID:
+            raise InvalidCharacterException("sequence holds a non-ACGT character")
+        return [int(c) for c in counts]
+
+    def insert_and_query_sequence(self, sequence):
+        """dbg.hh:327-340.  Serial semantics (each k-mer sees the earlier k-mers of the same
+        sequence), so the k-mers are issued one launch at a time; not a throughput path."""
+        hs = self.hasher.hashes(sequence if isinstance(sequence, str) else sequence.decode("ascii"))
+        return [self.S.insert_and_query(h.value()) for h in hs]
+
+    def get_kmer_counts(self, sequence):
+        return self.query_sequence(sequence)

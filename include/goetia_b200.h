@@ -1,0 +1,177 @@
+/*
+ * goetia_b200.h -- C ABI of the B200-native k-mer ingest backend (libgoetia_b200.so).
+ *
+ * goetia itself has no FFI for this path: the boundary in the reference is the C++ template
+ * pair  dBG<StorageType, ShifterType>  (include/goetia/dbg.hh:39-41), reached from Python
+ * through cppyy.  This header is the thin `extern "C"` layer that a GPU-backed StorageType /
+ * ShifterType pair sits on (see INTEGRATION.md for the C++ adapter a goetia maintainer adds,
+ * and goetia_b200/ for the Python mirror of the cppyy surface).  Every entry point cites the
+ * reference member(s) it stands in for; paths are relative to the goetia source tree.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; handles are opaque; no CUDA or torch types.
+ *   - functions returning int: 0 = ok, <0 = error (message via gt_last_error()).
+ *     functions returning int64_t: >=0 = count (k-mers consumed), <0 = error.
+ *     No exception crosses this boundary; the wrappers re-throw (reference error convention:
+ *     GoetiaException family, goetia.hh:140-178).
+ *   - one host thread drives one handle at a time (the reference dBG is not thread-safe
+ *     either: kmeriterator.hh:64-76 re-bases the graph's own shifter).
+ *   - "host" pointers are ordinary CPU memory (pinned memory makes the copies asynchronous);
+ *     "_dev" entry points take device pointers already resident in HBM and a CUDA stream
+ *     handle (void*, 0 = the library's own stream) and do not synchronise.
+ *   - sequences travel as one concatenated byte buffer `bases` plus `offsets[n_reads+1]`
+ *     (read r = bases[offsets[r] .. offsets[r+1])).  Per read the semantics are those of
+ *     FastxParser<DNA_SIMPLE> + InserterProcessor (parsing/readers.hh:150-219,
+ *     processors.hh:304-331): a/c/g/t are folded to upper case; a read holding any other byte
+ *     is skipped (status bit GT_READ_INVALID); a read shorter than K contributes 0 k-mers
+ *     (status bit GT_READ_SHORT) -- where the reference's dBG::insert_sequence would throw
+ *     SequenceLengthException (kmeriterator.hh:57-59) and the processor would swallow it.
+ *   - all hash / bin arithmetic is unsigned 64-bit and bit-exact with the reference.
+ */
+#ifndef GOETIA_B200_H
+#define GOETIA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GT_ABI_VERSION 1
+
+/* StorageType selector: BitStorage (storage/bitstorage.hh:93), ByteStorage
+ * (storage/bytestorage.hh:96), NibbleStorage (storage/nibblestorage.hh:89). */
+enum { GT_STORAGE_BIT = 0, GT_STORAGE_BYTE = 1, GT_STORAGE_NIBBLE = 2 };
+/* ShifterType selector: FwdLemireShifter / CanLemireShifter (hashing/hashshifter.hh:204-205). */
+enum { GT_SHIFTER_FWD = 0, GT_SHIFTER_CAN = 1 };
+/* How order-dependent outputs (is_new, n_unique) are produced -- SURVEY.md section 8a
+ * "sequential-equivalence rule".  Final table bytes are identical in every mode.
+ *   GT_MODE_BLIND : fire-and-forget updates; n_unique is NOT maintained (stats report it
+ *                   as of the last tracked batch); fastest.
+ *   GT_MODE_FAST  : a k-mer is credited as new when one of ITS atomic updates found the
+ *                   slot empty ("atomic winner"); equals the serial count except when two
+ *                   different k-mers of one batch collide on a fresh slot.
+ *   GT_MODE_EXACT : serial-order semantics (first toucher in read/k-mer order), identical
+ *                   to the reference's one-at-a-time loop. */
+enum { GT_MODE_BLIND = 0, GT_MODE_FAST = 1, GT_MODE_EXACT = 2 };
+/* per-read status bits */
+enum { GT_READ_OK = 0, GT_READ_SHORT = 1, GT_READ_INVALID = 2 };
+
+typedef struct gt_storage gt_storage; /* device-resident tables of one StorageType */
+typedef struct gt_batch gt_batch;     /* device-resident 2-bit packed read batch     */
+typedef struct gt_sketch gt_sketch;   /* device-resident scaled / bottom-k MinHash   */
+
+/* ---- library ------------------------------------------------------------------------ */
+int gt_abi_version(void);
+/* Select the CUDA device this process drives (one process per GPU).  Must precede any other
+ * call; repeated calls with the same device are no-ops. */
+int gt_init(int device);
+int gt_device_count(void);
+/* Last error message of the calling thread (sourmash.hpp:40-65 polls a last-error code the
+ * same way). */
+const char* gt_last_error(void);
+/* Blocks until all work queued by this library has finished. */
+int gt_synchronize(void);
+
+/* ---- table sizing ------------------------------------------------------------------- */
+/* get_n_primes_near_x (storage/storage.hh:166-190): the n largest primes strictly below x,
+ * descending.  Returns how many were written (can be < n for tiny x). */
+int gt_primes_near(uint32_t n, uint64_t x, uint64_t* out);
+
+/* ---- StorageType -------------------------------------------------------------------- */
+/* Storage(const std::vector<uint64_t>& tablesizes): bitstorage.hh:113-121,
+ * bytestorage.hh (ctor), nibblestorage.hh:140-149.  Tables are zero-initialised in HBM. */
+gt_storage* gt_storage_create(int kind, const uint64_t* tablesizes, int n_tables);
+void gt_storage_destroy(gt_storage* st);
+/* reset(): zero all tables and both counters (bitstorage.cc reset, nibblestorage.hh:179+). */
+int gt_storage_reset(gt_storage* st);
+int gt_storage_kind(const gt_storage* st);
+int gt_storage_n_tables(const gt_storage* st);             /* n_tables()      */
+int gt_storage_tablesizes(const gt_storage* st, uint64_t* out); /* get_tablesizes() */
+/* Bytes of table i exactly as the reference allocates them: size/8+1 (bitstorage.hh:143-156),
+ * size (bytestorage.hh:125-134), size/2+1 (nibblestorage.hh:166-177). */
+uint64_t gt_storage_table_bytes(const gt_storage* st, int i);
+/* get_raw_tables() (storage.hh:126): copy table i to host memory, byte-identical to the
+ * reference's table after the same inserts. */
+int gt_storage_download_table(gt_storage* st, int i, uint8_t* host_dst);
+/* load(): replace table i from host bytes (same layout); counters are NOT touched. */
+int gt_storage_upload_table(gt_storage* st, int i, const uint8_t* host_src);
+/* n_unique_kmers() / n_occupied() (storage.hh:119-120).  n_occupied is recomputed from
+ * table 0 (number of non-zero slots), which is what the reference's counter equals. */
+int gt_storage_stats(gt_storage* st, uint64_t* n_unique, uint64_t* n_occupied);
+int gt_storage_set_n_unique(gt_storage* st, uint64_t n_unique);
+/* BitStorage::update_from (bitstorage.cc:103-137): dst |= src, same table sizes. */
+int gt_storage_update_from(gt_storage* dst, const gt_storage* src);
+/* Raw device pointer of table i (for peer mapping / torch interop). */
+void* gt_storage_device_table(gt_storage* st, int i);
+
+/* Storage::insert / query / insert_and_query over a vector of hash values
+ * (bitstorage.hh:195-219, bitstorage.cc:78-100, bytestorage.cc:60-150,
+ * nibblestorage.cc:60-130).  is_new (uint8 per hash) may be NULL.  Host pointers. */
+int gt_insert_hashes(gt_storage* st, const uint64_t* hashes, uint64_t n, int mode, uint8_t* is_new);
+int gt_query_hashes(gt_storage* st, const uint64_t* hashes, uint64_t n, int16_t* counts);
+
+/* ---- ShifterType -------------------------------------------------------------------- */
+/* KmerIterator<Shifter> over every read (hashing/kmeriterator.hh:64-123).  fw[] (and rc[]
+ * for GT_SHIFTER_CAN; may be NULL for FWD) receive one value per k-mer, reads back to back
+ * (read r's k-mers start at the running sum of max(0, len-K+1) over valid earlier reads).
+ * status (uint8 per read) may be NULL.  Returns the total number of k-mers. */
+int64_t gt_hash_sequences(int shifter, int K, const char* bases, const uint64_t* offsets,
+                          uint64_t n_reads, uint64_t* fw, uint64_t* rc, uint8_t* status);
+
+/* ---- dBG<Storage, Shifter> batch members (host buffers) ------------------------------- */
+/* dBG::insert_sequence over a batch (dbg.hh:296-305; with n_new: :307-318).  Returns the
+ * total k-mers consumed (sum of len-K+1).  n_new_per_read (uint64 per read) needs
+ * GT_MODE_EXACT and may be NULL.  status may be NULL. */
+int64_t gt_insert_sequences(gt_storage* st, int shifter, int K, const char* bases,
+                            const uint64_t* offsets, uint64_t n_reads, int mode,
+                            uint64_t* n_new_per_read, uint8_t* status);
+/* dBG::query_sequence over a batch (dbg.hh:349-362): counts laid out like gt_hash_sequences. */
+int64_t gt_query_sequences(gt_storage* st, int shifter, int K, const char* bases,
+                           const uint64_t* offsets, uint64_t n_reads, int16_t* counts,
+                           uint8_t* status);
+/* DiginormFilter::median_count_at_least per read (diginorm.hh:35-68): pass[r] = 1 iff at
+ * least unsigned(0.5 + float(n_kmers)/2) k-mers of read r have count >= cutoff.  Skipped
+ * reads get 0. */
+int64_t gt_median_count_at_least(gt_storage* st, int shifter, int K, const char* bases,
+                                 const uint64_t* offsets, uint64_t n_reads, uint32_t cutoff,
+                                 uint8_t* pass, uint8_t* status);
+
+/* ---- device-resident batches (the parsing-to-device pipeline's product) --------------- */
+/* Upload + validate + 2-bit pack a batch (A=0 C=1 G=2 T=3; flat base p at bits 2*(p%32) of
+ * 64-bit word p/32).  The batch stays in HBM until destroyed and can be inserted / queried
+ * any number of times. */
+gt_batch* gt_batch_pack(const char* bases, const uint64_t* offsets, uint64_t n_reads);
+/* Same, but from device-resident ASCII (d_bases, d_offsets are device pointers). */
+gt_batch* gt_batch_pack_dev(const void* d_bases, const void* d_offsets, uint64_t n_reads,
+                            uint64_t n_bases);
+void gt_batch_destroy(gt_batch* b);
+uint64_t gt_batch_n_reads(const gt_batch* b);
+uint64_t gt_batch_n_bases(const gt_batch* b);
+/* total k-mers a K-mer walk of this batch consumes */
+int64_t gt_batch_n_kmers(gt_batch* b, int K);
+int gt_batch_status(gt_batch* b, int K, uint8_t* status);
+/* Queue insert / query of a resident batch on `stream` (0 = library stream); asynchronous. */
+int64_t gt_insert_batch(gt_storage* st, int shifter, int K, gt_batch* b, int mode, void* stream);
+
+/* ---- SourmashSketch (sketches/sourmash_sketch.hh:24-82) -------------------------------- */
+/* Sketch(n, K, is_protein=false, dayhoff=false, hp=false, seed, scaled):
+ * max_hash_from_scaled (:52-61) is applied by the caller via gt_max_hash_from_scaled. */
+uint64_t gt_max_hash_from_scaled(uint64_t scaled);
+gt_sketch* gt_sketch_create(uint32_t num, int K, uint32_t seed, uint64_t max_hash);
+void gt_sketch_destroy(gt_sketch* sk);
+/* Sketch::insert_sequence over a batch (:71-81; add_sequence(seq, force=true)): windows with
+ * a byte outside ACGTacgt are skipped.  Returns sum of len-K+1 over reads with len >= K. */
+int64_t gt_sketch_add_sequences(gt_sketch* sk, const char* bases, const uint64_t* offsets,
+                                uint64_t n_reads);
+/* MinHash::add_hash / merge (sourmash.hpp:80, :97) */
+int gt_sketch_add_hashes(gt_sketch* sk, const uint64_t* hashes, uint64_t n);
+int gt_sketch_merge(gt_sketch* dst, gt_sketch* src);
+/* MinHash::size / mins (sourmash.hpp:116, :151-157): ascending, duplicate-free. */
+int64_t gt_sketch_size(gt_sketch* sk);
+int64_t gt_sketch_mins(gt_sketch* sk, uint64_t* out, uint64_t capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOETIA_B200_H */
