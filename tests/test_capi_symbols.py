@@ -1,0 +1,79 @@
+"""CPU test: the C-ABI library builds, loads, and exports every symbol include/goetia_b200.h declares.
+No compute call is made (there is no GPU here)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "goetia_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(gt_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_builds_and_exports_header():
+    from goetia_b200 import build, _capi
+    build.build()
+    L = _capi.load()
+    names = _declared()
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(L, n), "libgoetia_b200.so does not export " + n
+    # and the binding table covers exactly the header
+    assert sorted(_capi.SIGNATURES) == names
+    assert L.gt_abi_version() == 1
+
+
+def test_host_only_entry_points():
+    from goetia_b200 import get_n_primes_near_x, _capi
+    assert get_n_primes_near_x(4, 10**6) == [999983, 999979, 999961, 999959]
+    assert get_n_primes_near_x(1, 1) == [1]
+    assert _capi.load().gt_max_hash_from_scaled(1000) == 18446744073709552
+    assert _capi.load().gt_max_hash_from_scaled(0) == 0
+    assert _capi.load().gt_max_hash_from_scaled(1) == 2**64 - 1
+
+
+def test_compute_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import goetia_b200 as gb
+    with pytest.raises(gb.GoetiaB200Error):
+        gb.BitStorage(1000, 4)
+
+
+def test_product_never_imports_oracle():
+    """The product package must not reference the checker."""
+    pkg = os.path.join(ROOT, "goetia_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".inc", ".h", ".hh")):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), os.path.join(dp, f)
+
+
+def test_host_cursor_shifter_matches_golden(golden):
+    """hash_base / shift_right / shift_left cursor members (host latency path)."""
+    from goetia_b200.hashing import CanLemireShifter, FwdLemireShifter
+    k = golden["kat"]
+    s = CanLemireShifter(k["K"])
+    h = s.hash_base(k["seq"])
+    assert (str(h.fw_hash), str(h.rc_hash)) == (k["fw"], k["rc"])
+    seq = golden["hash_vectors"]["seq"]
+    for K in (21, 31, 64, 101):
+        exp = golden["hash_vectors"]["cases"]["K%d_can1" % K]
+        sh = CanLemireShifter(K)
+        h = sh.hash_base(seq)
+        got = [h]
+        for i in range(1, 3):
+            got.append(sh.shift_right(seq[i - 1], seq[i + K - 1]))
+        assert [str(g.fw_hash) for g in got] == exp["fw_head"]
+        assert [str(g.rc_hash) for g in got] == exp["rc_head"]
+        # shift_left undoes shift_right (reference tests/test_hashing.py:303-329)
+        back = sh.shift_left(seq[1], seq[2 + K - 1])
+        assert (str(back.fw_hash), str(back.rc_hash)) == (exp["fw_head"][1], exp["rc_head"][1])
+        f = FwdLemireShifter(K)
+        assert str(f.hash_base(seq).value()) == golden["hash_vectors"]["cases"]["K%d_can0" % K]["fw_head"][0]
