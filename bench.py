@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- k-mers inserted per second on the BASELINE.json workload (one JSON line).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c3|c1|c2|c5]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path (2-bit pack -> canonical rolling hash -> insert into the
+probabilistic tables) over the whole synthetic read set of the workload.  The default workload
+is BASELINE.json configs[2] -- the one the metric's target ("BitStorage K=31 insert") and its
+1/2/4/8-GPU scaling are quoted on, and it fits one B200: dBG<BitStorage, CanLemireShifter>,
+K=31, 4 tables x ~8e9 bits (get_n_primes_near_x(4, 8e9)), 50 M synthetic 150 bp reads
+(6.0e9 k-mers per step).
+
+  value : device-timed (CUDA events on the library's compute stream), reads resident in HBM as
+          ASCII + offsets when the timed region starts.
+  e2e   : the same step through the host-buffer C-ABI call (gt_insert_sequences on pinned host
+          ASCII, H2D copies inside the timed region, k-mer count read back), wall clock.
+  roofline      : algorithmic 256 B/k-mer (4 x (32 B sector read + 32 B write-back), SURVEY.md
+                  section 8d) over the summed device time of the two insert kernels.
+  cpu_baseline  : the unmodified reference (oracle/_ref, compiled from /root/reference) -- or
+                  the plain-C port when that .so is absent -- on the box's host cores over a
+                  bounded sample of the same reads.
+
+--impl reference times that CPU implementation as its own arm (rank 0 only).
+The oracle is only ever the checker / the CPU baseline here, never the measured product path.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ALGO_BYTES_PER_KMER_PER_TABLE = 64  # 32 B sector read + 32 B write-back
+
+WORKLOADS = {
+    # name: (storage kind, K, table x, n_tables, total reads, read length, seed, description)
+    "c3": (0, 31, int(8e9), 4, 50_000_000, 150, 44,
+           "C3: dBG<BitStorage,CanLemireShifter> K=31, 4 tables x 8e9 bits, 50M x 150bp synthetic reads"),
+    "c1": (0, 31, int(1e9), 4, 100_000, 150, 42,
+           "C1: dBG<BitStorage,CanLemireShifter> K=31, BitStorage(1e9,4), 100k x 150bp synthetic reads"),
+    "c2": (1, 21, int(4e9), 4, 20_000_000, 150, 43,
+           "C2: dBG<ByteStorage,CanLemireShifter> K=21, ByteStorage(4e9,4), 20M x 150bp synthetic reads (insert)"),
+    "c5": (2, 25, int(8e9), 4, 1_000_000, 10_000, 46,
+           "C5: dBG<NibbleStorage,CanLemireShifter> K=25, NibbleStorage(8e9,4), 1M x 10kb synthetic reads"),
+}
+SUB_BATCH_BASES = 900_000_000  # reads are fed to the library in sub-batches of about this many bases
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--reads", type=int, default=0, help="override the workload's read count (smoke runs)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 100 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synth_reads_device(torch, n_reads, read_len, seed, device):
+    """Uniform random ACGT reads generated on the device (torch Philox, seed stated in config)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    n = n_reads * read_len
+    out = torch.empty(n, dtype=torch.uint8, device=device)
+    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=device)
+    step = 1 << 26
+    for i in range(0, n, step):
+        m = min(step, n - i)
+        codes = torch.randint(0, 4, (m,), dtype=torch.int64, device=device, generator=g)
+        out[i:i + m] = lut[codes]
+    return out
+
+
+def cpu_reference_rate(kind, K, sizes, bases, offsets, budget_s, threads):
+    """Time the CPU implementation (unmodified reference if built, else the plain-C port) on a
+    bounded prefix of the reads.  Returns dict(value, cores, kind, sample)."""
+    from oracle import binding
+    n_total = offsets.size - 1
+    if binding.have_ref():
+        impl, kname = binding.Ref(kind, 1, K, sizes), "reference"
+        use_threads = threads if kind == 0 else 1  # only BitStorage is bit-reproducible multi-threaded
+    else:
+        impl, kname = binding.Port(kind, 1, K, sizes), "port"
+        use_threads = 1
+
+    def run(r0, r1):
+        b = bases[int(offsets[r0]):int(offsets[r1])]
+        o = offsets[r0:r1 + 1] - offsets[r0]
+        if kname == "reference":
+            nk, secs = impl.insert_reads(b, o, n_threads=use_threads)
+        else:
+            nk, secs = impl.insert_reads(b, o)
+        return nk, secs
+
+    probe = min(n_total, 50_000)
+    nk, secs = run(0, probe)  # also faults the tables' pages in
+    rate = nk / max(secs, 1e-9)
+    kpr = max(1.0, nk / probe)
+    sample = int(min(n_total - probe, max(probe, rate * budget_s / kpr)))
+    if sample <= 0:
+        sample, r0 = probe, 0
+    else:
+        r0 = probe
+    nk, secs = run(r0, r0 + sample)
+    impl.close()
+    return {"value": nk / secs, "unit": "k-mers/s", "cores": use_threads, "kind": kname,
+            "sample": "%d reads (%d k-mers) of the same synthetic set, %.1f s, %s"
+                      % (sample, nk, secs, "dBG::insert_sequence per read, one dBG copy per thread over one shared "
+                         "storage" if use_threads > 1 else "dBG::insert_sequence per read, one thread")}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    kind, K, x, n_tables, total_reads, read_len, seed, desc = WORKLOADS[args.workload]
+    if args.reads:
+        total_reads = args.reads
+    kpr = read_len - K + 1
+
+    if args.impl == "reference":
+        return reference_arm(args, rank, world, kind, K, x, n_tables, total_reads, read_len, seed, desc)
+
+    import torch
+    import goetia_b200 as gb
+    from goetia_b200 import _capi
+
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    gb.init(local_rank)
+    L = _capi.lib()
+    sizes = gb.get_n_primes_near_x(n_tables, x)
+
+    if world > 1:
+        from goetia_b200 import shard
+        return shard.bench_multi_gpu(args, rank, world, local_rank, WORKLOADS[args.workload], total_reads)
+
+    # ---- inputs: resident ASCII sub-batches ------------------------------------------------------
+    reads_per_sub = max(1, min(total_reads, SUB_BATCH_BASES // read_len))
+    subs = []
+    r = 0
+    while r < total_reads:
+        n = min(reads_per_sub, total_reads - r)
+        subs.append((synth_reads_device(torch, n, read_len, seed + 1000 * len(subs), dev), n))
+        r += n
+    offs = torch.arange(reads_per_sub + 1, dtype=torch.int64, device=dev) * read_len
+    torch.cuda.synchronize()
+    storage = [gb.BitStorage, gb.ByteStorage, gb.NibbleStorage][kind](sizes)
+    graph = gb.dBG[type(storage), gb.CanLemireShifter].build(storage, K)
+
+    def step_resident():
+        nk = 0
+        for b, n in subs:
+            nk += graph.insert_sequences_dev(b.data_ptr(), offs.data_ptr(), n, n * read_len, mode=gb.MODE_BLIND)
+        storage.flush()
+        return nk
+
+    kmers_per_step = total_reads * kpr
+    for _ in range(args.warmup):
+        assert step_resident() == kmers_per_step
+    L.gt_synchronize()
+    _capi.check(L.gt_profile_enable(1), "gt_profile_enable")
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = L.gt_launch_count()
+    _capi.check(L.gt_timer_record(0), "gt_timer_record")
+    for _ in range(args.steps):
+        step_resident()
+    _capi.check(L.gt_timer_record(1), "gt_timer_record")
+    ms = L.gt_timer_elapsed_ms(0, 1)
+    L.gt_synchronize()
+    launches = int(L.gt_launch_count() - launches0)
+    clocks = sampler.stop()
+    prof_ms = np.zeros(3, dtype=np.float64)
+    prof_n = np.zeros(3, dtype=np.uint64)
+    _capi.check(L.gt_profile_get(prof_ms.ctypes.data, prof_n.ctypes.data), "gt_profile_get")
+    L.gt_profile_enable(0)
+    value = kmers_per_step * args.steps / (ms / 1e3)
+
+    # ---- property check at full size (the oracle cannot run 6e9 k-mers in bench time) -----------
+    info = storage.pending_info()
+    sample_b = subs[0][0][:2000 * read_len].cpu().numpy()
+    sample_o = np.arange(2001, dtype=np.uint64) * np.uint64(read_len)
+    q = graph.query_sequences(sample_b, sample_o)
+    present = bool((q >= 1).all())
+    n_occ = storage.n_occupied()
+
+    # ---- e2e: host buffers through the C ABI ------------------------------------------------------
+    e2e = None
+    host_b = host_o = None
+    if not args.no_e2e:
+        host_b = torch.empty(total_reads * read_len, dtype=torch.uint8, pin_memory=True)
+        p = 0
+        for b, n in subs:
+            host_b[p:p + n * read_len].copy_(b)
+            p += n * read_len
+        host_o = torch.empty(total_reads + 1, dtype=torch.int64, pin_memory=True)
+        host_o.copy_(torch.arange(total_reads + 1, dtype=torch.int64) * read_len)
+        torch.cuda.synchronize()
+        hb, ho = host_b.numpy(), host_o.numpy().view(np.uint64)
+        os.environ.setdefault("GT_CHUNK_BASES", str(256 << 20))
+
+        def step_host():
+            nk = graph.insert_sequences(hb, ho, mode=gb.MODE_BLIND)  # returns the k-mer count read back from the device
+            storage.flush()
+            return nk
+
+        for _ in range(min(args.warmup, 2)):
+            assert step_host() == kmers_per_step
+        L.gt_synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host()
+        L.gt_synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {"value": kmers_per_step * args.steps / dt, "unit": "k-mers/s",
+               "h2d_bytes_per_step": int(hb.nbytes + ho.nbytes), "d2h_bytes_per_step": 8,
+               "ms_per_step": dt * 1e3 / args.steps,
+               "api": "gt_insert_sequences(host ASCII, host offsets) + gt_storage_flush, pinned host memory"}
+
+    # ---- roofline -----------------------------------------------------------------------------------
+    peak, peak_src = measured_peak()
+    ins_ms = float(prof_ms[0] + prof_ms[1] + prof_ms[2])
+    algo_bytes = ALGO_BYTES_PER_KMER_PER_TABLE * n_tables
+    achieved = kmers_per_step * args.steps * algo_bytes / (ins_ms / 1e3) / 1e9 if ins_ms > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(args.workload)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "kernel": "k_bucket + k_apply (the two halves of one insert: bucket by table slice, apply per slice)",
+                "algorithmic_bytes_per_kmer": algo_bytes,
+                "kernels": {name: {"launches": int(prof_n[i]), "ms_total": float(prof_ms[i]),
+                                   "ms_per_launch": float(prof_ms[i] / max(1, int(prof_n[i]))),
+                                   "share_of_step": float(prof_ms[i] / ms) if ms > 0 else 0.0}
+                            for i, name in enumerate(("k_bucket", "k_apply", "k_walk")) if prof_n[i]}}
+
+    # ---- CPU baseline ---------------------------------------------------------------------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        nb = min(total_reads, 4_000_000)
+        if host_b is not None:
+            cb = host_b.numpy()[:nb * read_len]
+        else:
+            cb = subs[0][0][:nb * read_len].cpu().numpy()
+            nb = cb.size // read_len
+        co = np.arange(nb + 1, dtype=np.uint64) * np.uint64(read_len)
+        del storage, graph
+        cpu = cpu_reference_rate(kind, K, sizes, cb, co, budget_s=15.0, threads=os.cpu_count() or 1)
+
+    out = {
+        "metric": "k-mers inserted/sec (device-timed)", "value": value, "unit": "k-mers/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": desc if not args.reads else desc + " [reads overridden: %d]" % total_reads,
+                   "K": K, "tablesizes": sizes, "reads": total_reads, "read_len": read_len,
+                   "kmers_per_step": kmers_per_step, "mode": "GT_MODE_BLIND (write-combined)",
+                   "sub_batches": len(subs), "slice_shift": info["slice_shift"], "n_buckets": info["n_buckets"],
+                   "pending_entries": info["entries"], "bucket_overflow_updates": info["n_direct"],
+                   "seed": seed, "generator": "torch.randint on device (Philox)",
+                   "l2": "inputs larger than L2 (%.1f GB reads + %.1f GB tables + %.1f GB update store per step)"
+                         % (total_reads * read_len / 1e9, sum(sizes) / 8e9 if kind == 0 else sum(sizes) / 1e9,
+                            info["entries"] * 4 / 1e9),
+                   "tables": "accumulate across steps (no reset): RED.OR / saturating-CAS work is the same on a full table"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "check": {"sample_reads_all_present": present, "n_occupied": n_occ},
+    }
+    print(json.dumps(out))
+    return 0
+
+
+def reference_arm(args, rank, world, kind, K, x, n_tables, total_reads, read_len, seed, desc):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
+    if rank != 0:
+        return 0
+    from oracle import binding
+    threads = os.cpu_count() or 1
+    sizes = binding.Port.primes_near(n_tables, x)
+    have_ref = binding.have_ref()
+    impl = binding.Ref(kind, 1, K, sizes) if have_ref else binding.Port(kind, 1, K, sizes)
+    use_threads = threads if (have_ref and kind == 0) else 1
+    rng = np.random.default_rng(seed)
+    kpr = read_len - K + 1
+
+    def make(n):
+        codes = rng.integers(0, 4, n * read_len, dtype=np.uint8)
+        return (np.frombuffer(b"ACGT", dtype=np.uint8)[codes],
+                np.arange(n + 1, dtype=np.uint64) * np.uint64(read_len))
+
+    def run(b, o):
+        if have_ref:
+            return impl.insert_reads(b, o, n_threads=use_threads)
+        return impl.insert_reads(b, o)
+
+    b, o = make(20_000)
+    nk, secs = run(b, o)  # calibrate (and fault the tables in)
+    rate = nk / max(secs, 1e-9)
+    n_steps = args.steps + args.warmup
+    per_step_s = min(12.0, 150.0 / max(1, n_steps))
+    n = int(max(20_000, min(total_reads, rate * per_step_s / kpr)))
+    b, o = make(n)
+    for _ in range(args.warmup):
+        run(b, o)
+    tot_k, tot_s = 0, 0.0
+    for _ in range(args.steps):
+        nk, secs = run(b, o)
+        tot_k += nk
+        tot_s += secs
+    value = tot_k / tot_s
+    sample = "%d reads (%d k-mers) per step of the workload's synthetic shape" % (n, n * kpr)
+    out = {"impl": "reference", "metric": "k-mers inserted/sec (device-timed)", "value": value, "unit": "k-mers/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_s * 1e3 / args.steps,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+           "config": {"workload": desc, "K": K, "tablesizes": sizes, "reads_per_step": n, "read_len": read_len,
+                      "note": "CPU implementation on the host cores; each step is a bounded sample of the workload"},
+           "cpu_baseline": {"value": value, "unit": "k-mers/s", "cores": use_threads,
+                            "kind": "reference" if have_ref else "port", "sample": sample},
+           "e2e": {"value": value, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

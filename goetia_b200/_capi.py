@@ -59,6 +59,15 @@ SIGNATURES = {
     "gt_batch_n_kmers": (C.c_int64, [C.c_void_p, C.c_int]),
     "gt_batch_status": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "gt_insert_batch": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "gt_insert_sequences_dev": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64,
+                                            C.c_uint64, C.c_int]),
+    "gt_storage_flush": (C.c_int, [C.c_void_p]),
+    "gt_storage_pending_info": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gt_launch_count": (C.c_uint64, []),
+    "gt_timer_record": (C.c_int, [C.c_int]),
+    "gt_timer_elapsed_ms": (C.c_double, [C.c_int, C.c_int]),
+    "gt_profile_enable": (C.c_int, [C.c_int]),
+    "gt_profile_get": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gt_max_hash_from_scaled": (C.c_uint64, [C.c_uint64]),
     "gt_sketch_create": (C.c_void_p, [C.c_uint32, C.c_int, C.c_uint32, C.c_uint64]),
     "gt_sketch_destroy": (None, [C.c_void_p]),

@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "capi.cu")
-DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("kernels.cuh", "sketch.cuh", "sketch_host.inc", "exact.cuh",
-                                                          "shard.cuh")] + [os.path.join(ROOT, "include", "goetia_b200.h")]
+DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("kernels.cuh", "sketch.cuh", "sketch_host.inc", "bucket.cuh",
+                                                          "bucket_host.inc")] + [os.path.join(ROOT, "include", "goetia_b200.h")]
 OUT = os.path.join(HERE, "libgoetia_b200.so")
 
 NVCC_FLAGS = [

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -16,6 +17,7 @@
 
 #include "../../include/goetia_b200.h"
 #include "kernels.cuh"
+#include "bucket.cuh"
 #include "sketch.cuh"
 
 using namespace gt;
@@ -80,6 +82,9 @@ struct DevBuf {
 
 struct Slot {
     cudaStream_t stream = nullptr;
+    cudaEvent_t packed = nullptr;    // recorded on `stream` when the chunk is packed
+    cudaEvent_t consumed = nullptr;  // recorded on the compute stream when the chunk's buffers are free again
+    bool consumed_pending = false;
     DevBuf ascii, words, offsets, flags, coarse, nmask, kcount, koff, partial, hits, out16, out64a, out64b, out8;
 };
 
@@ -94,6 +99,44 @@ struct Context {
 };
 static Context g_ctx;
 static std::mutex g_mu;
+static unsigned long long g_launches = 0;  // kernels of this library launched so far (gt_launch_count)
+
+// Optional per-kernel device timing (gt_profile_*): CUDA event pairs around the launches of the
+// two insert kernels on the stream they run on; resolved lazily.  Off by default.
+enum { PROF_BUCKET = 0, PROF_APPLY = 1, PROF_WALK = 2, PROF_KINDS = 3 };
+struct ProfSpan { cudaEvent_t a, b; int kind; };
+static bool g_prof_on = false;
+static std::vector<ProfSpan> g_prof_open;
+static std::vector<cudaEvent_t> g_prof_pool;
+static double g_prof_ms[PROF_KINDS] = {0, 0, 0};
+static unsigned long long g_prof_n[PROF_KINDS] = {0, 0, 0};
+static cudaEvent_t prof_event() {
+    cudaEvent_t e = nullptr;
+    if (!g_prof_pool.empty()) { e = g_prof_pool.back(); g_prof_pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+}
+struct ProfScope {  // brackets one launch
+    cudaStream_t s; int kind; cudaEvent_t a = nullptr;
+    ProfScope(int kind_, cudaStream_t s_) : s(s_), kind(kind_) {
+        if (g_prof_on) { a = prof_event(); cudaEventRecord(a, s); }
+    }
+    ~ProfScope() {
+        if (a) { cudaEvent_t b = prof_event(); cudaEventRecord(b, s); g_prof_open.push_back({a, b, kind}); }
+    }
+};
+static void prof_resolve() {
+    for (auto& sp : g_prof_open) {
+        float ms = 0;
+        if (cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+            g_prof_ms[sp.kind] += ms;
+            g_prof_n[sp.kind] += 1;
+        }
+        g_prof_pool.push_back(sp.a);
+        g_prof_pool.push_back(sp.b);
+    }
+    g_prof_open.clear();
+}
 
 static int ensure_ctx() {
     if (g_ctx.ready) return 0;
@@ -138,7 +181,11 @@ extern "C" int gt_init(int device) {
     if (prop.major < 10) return fail("gt_init: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     g_ctx.sms = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&g_ctx.main, cudaStreamNonBlocking));
-    for (auto& s : g_ctx.slot) CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    for (auto& s : g_ctx.slot) {
+        CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&s.packed, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
+    }
     CU(cudaMalloc(&g_ctx.d_scratch, 8 * sizeof(unsigned long long)));
     CU(cudaMemset(g_ctx.d_scratch, 0, 8 * sizeof(unsigned long long)));
     CU(cudaMallocHost(&g_ctx.h_scratch, 8 * sizeof(unsigned long long)));
@@ -183,7 +230,12 @@ extern "C" int gt_primes_near(uint32_t n, uint64_t x, uint64_t* out) {
 // ------------------------------------------------------------------------------------------
 // storage
 // ------------------------------------------------------------------------------------------
+struct Pending;
+static void pending_free(Pending* p);
+static int pending_flush_sync(gt_storage* st);
+static int pending_discard(gt_storage* st);
 struct gt_storage {
+    Pending* pend = nullptr;  // write-combining store of not-yet-applied blind inserts (bucket_host.inc)
     int kind = 0;
     int n = 0;
     uint64_t sizes[MAX_TABLES];
@@ -247,12 +299,15 @@ extern "C" void gt_storage_destroy(gt_storage* st) {
     for (int i = 0; i < st->n; ++i)
         if (st->ts.ptr[i]) cudaFree(st->ts.ptr[i]);
     if (st->d_n_unique) cudaFree(st->d_n_unique);
+    pending_free(st->pend);
     delete st;
 }
 
 extern "C" int gt_storage_reset(gt_storage* st) {
     if (ensure_ctx()) return -1;
     if (!st) return fail("gt_storage_reset: NULL storage");
+    CU(cudaDeviceSynchronize());
+    if (pending_discard(st)) return -1;
     for (int i = 0; i < st->n; ++i) CU(cudaMemsetAsync(st->ts.ptr[i], 0, st->alloc_bytes[i], g_ctx.main));
     CU(cudaMemsetAsync(st->d_n_unique, 0, sizeof(unsigned long long), g_ctx.main));
     CU(cudaStreamSynchronize(g_ctx.main));
@@ -272,12 +327,14 @@ extern "C" uint64_t gt_storage_table_bytes(const gt_storage* st, int i) {
 }
 extern "C" void* gt_storage_device_table(gt_storage* st, int i) {
     if (!st || i < 0 || i >= st->n) return nullptr;
+    if (pending_flush_sync(st)) return nullptr;
     return st->ts.ptr[i];
 }
 
 extern "C" int gt_storage_download_table(gt_storage* st, int i, uint8_t* host_dst) {
     if (ensure_ctx()) return -1;
     if (!st || !host_dst || i < 0 || i >= st->n) return fail("gt_storage_download_table: bad argument");
+    if (pending_flush_sync(st)) return -1;
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(host_dst, st->ts.ptr[i], st->ref_bytes[i], cudaMemcpyDeviceToHost));
     return 0;
@@ -286,6 +343,7 @@ extern "C" int gt_storage_download_table(gt_storage* st, int i, uint8_t* host_ds
 extern "C" int gt_storage_upload_table(gt_storage* st, int i, const uint8_t* host_src) {
     if (ensure_ctx()) return -1;
     if (!st || !host_src || i < 0 || i >= st->n) return fail("gt_storage_upload_table: bad argument");
+    if (pending_flush_sync(st)) return -1;
     CU(cudaDeviceSynchronize());
     CU(cudaMemset(st->ts.ptr[i], 0, st->alloc_bytes[i]));
     CU(cudaMemcpy(st->ts.ptr[i], host_src, st->ref_bytes[i], cudaMemcpyHostToDevice));
@@ -302,6 +360,7 @@ static int grid_for(uint64_t items, int per_block, int blocks_per_sm) {
 extern "C" int gt_storage_stats(gt_storage* st, uint64_t* n_unique, uint64_t* n_occupied) {
     if (ensure_ctx()) return -1;
     if (!st) return fail("gt_storage_stats: NULL storage");
+    if (pending_flush_sync(st)) return -1;
     CU(cudaDeviceSynchronize());
     cudaStream_t s = g_ctx.main;
     unsigned long long* d_occ = g_ctx.d_scratch + 1;
@@ -311,7 +370,7 @@ extern "C" int gt_storage_stats(gt_storage* st, uint64_t* n_unique, uint64_t* n_
     int grid = grid_for(n_words, 256 * 8, 8);
     if (st->kind == 0) k_count_occupied<0><<<grid, 256, 0, s>>>(st->ts.ptr[0], n_words, st->sizes[0], d_occ);
     else if (st->kind == 1) k_count_occupied<1><<<grid, 256, 0, s>>>(st->ts.ptr[0], n_words, st->sizes[0], d_occ);
-    else k_count_occupied<2><<<grid, 256, 0, s>>>(st->ts.ptr[0], n_words, st->sizes[0], d_occ);
+    else k_count_occupied<2><<<grid, 256, 0, s>>>(st->ts.ptr[0], n_words, st->sizes[0], d_occ); ++g_launches;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(g_ctx.h_scratch + 1, d_occ, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(g_ctx.h_scratch + 2, st->d_n_unique, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -337,10 +396,11 @@ extern "C" int gt_storage_update_from(gt_storage* dst, const gt_storage* src) {
         return fail("gt_storage_update_from: only BitStorage can be unioned (bitstorage.cc:103-137)");
     if (dst->n != src->n || memcmp(dst->sizes, src->sizes, sizeof(uint64_t) * dst->n) != 0)
         return fail("both nodegraphs must have same table sizes");
+    if (pending_flush_sync(dst) || pending_flush_sync(const_cast<gt_storage*>(src))) return -1;
     CU(cudaDeviceSynchronize());
     for (int i = 0; i < dst->n; ++i) {
         uint64_t n_words = dst->alloc_bytes[i] / 4;
-        k_or_tables<<<grid_for(n_words, 256 * 4, 8), 256, 0, g_ctx.main>>>(dst->ts.ptr[i], src->ts.ptr[i], n_words);
+        k_or_tables<<<grid_for(n_words, 256 * 4, 8), 256, 0, g_ctx.main>>>(dst->ts.ptr[i], src->ts.ptr[i], n_words); ++g_launches;
     }
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(g_ctx.main));
@@ -364,7 +424,10 @@ static int launch_walk_t(const WalkArgs& a, const TableSet& ts, cudaStream_t s) 
     uint64_t n_tiles = (a.n_bases + TILE_POS - 1) / TILE_POS;
     if (n_tiles == 0) return 0;
     int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)g_ctx.sms * occ);
-    kern<<<grid, TILE_THREADS, smem, s>>>(a, ts);
+    {
+        ProfScope ps(PROF_WALK, s);
+        kern<<<grid, TILE_THREADS, smem, s>>>(a, ts); ++g_launches;
+    }
     CU(cudaGetLastError());
     return 0;
 }
@@ -420,11 +483,11 @@ static int pack_on_device(const uint8_t* d_ascii, const uint64_t* d_offsets, uin
     if (n_words_alloc > n_words) CU(cudaMemsetAsync(d_words + n_words, 0, (n_words_alloc - n_words) * 8, s));
     if (d_nmask && n_words_alloc > n_words) CU(cudaMemsetAsync(d_nmask + n_words, 0, (n_words_alloc - n_words) * 4, s));
     if (n_words) {
-        k_pack<<<grid_for(n_words, 256, 16), 256, 0, s>>>(d_ascii, n_bases, d_offsets, n_reads, base0, d_words, n_words, d_flags, d_nmask);
+        k_pack<<<grid_for(n_words, 256, 16), 256, 0, s>>>(d_ascii, n_bases, d_offsets, n_reads, base0, d_words, n_words, d_flags, d_nmask); ++g_launches;
         CU(cudaGetLastError());
     }
     if (n_reads) {
-        k_coarse<<<grid_for(n_reads, 256, 16), 256, 0, s>>>(d_offsets, n_reads, base0, d_coarse);
+        k_coarse<<<grid_for(n_reads, 256, 16), 256, 0, s>>>(d_offsets, n_reads, base0, d_coarse); ++g_launches;
         CU(cudaGetLastError());
     }
     return 0;
@@ -444,6 +507,8 @@ static WalkArgs make_args(const gt_batch& b, int K) {
     a.K = K;
     return a;
 }
+
+#include "bucket_host.inc"
 
 // Stage one chunk of host reads [r0, r1) into slot `sl` and pack it.  Fills `view`.
 static int stage_chunk(Slot& sl, const char* bases, const uint64_t* offsets, uint64_t r0, uint64_t r1, gt_batch& view,
@@ -581,11 +646,11 @@ extern "C" gt_batch* gt_batch_pack(const char* bases, const uint64_t* offsets, u
         ok = ok && cudaMemcpyAsync(sl.ascii.p, bases + base0 + p, nb, cudaMemcpyHostToDevice, sl.stream) == cudaSuccess;
         uint64_t nw = (nb + 31) / 32;
         k_pack<<<grid_for(nw, 256, 16), 256, 0, sl.stream>>>(sl.ascii.as<uint8_t>(), nb, b->d_offsets, n_reads, p,
-                                                             b->d_words + p / 32, nw, b->d_flags, nullptr);
+                                                             b->d_words + p / 32, nw, b->d_flags, nullptr); ++g_launches;
         ok = ok && cudaGetLastError() == cudaSuccess;
     }
     if (ok && n_reads) {
-        k_coarse<<<grid_for(n_reads, 256, 16), 256, 0, g_ctx.main>>>(b->d_offsets, n_reads, 0, b->d_coarse);
+        k_coarse<<<grid_for(n_reads, 256, 16), 256, 0, g_ctx.main>>>(b->d_offsets, n_reads, 0, b->d_coarse); ++g_launches;
         ok = cudaGetLastError() == cudaSuccess;
     }
     ok = ok && cudaDeviceSynchronize() == cudaSuccess;
@@ -605,7 +670,7 @@ static int64_t batch_kmers(const gt_batch& b, int K, uint64_t* d_kcount, uint8_t
     unsigned long long* d_tot = g_ctx.d_scratch;
     CU(cudaMemsetAsync(d_tot, 0, sizeof(unsigned long long), s));
     if (b.n_reads) {
-        k_kmer_counts<<<grid_for(b.n_reads, 256, 16), 256, 0, s>>>(b.d_offsets, b.n_reads, K, b.d_flags, d_kcount, d_status, d_tot);
+        k_kmer_counts<<<grid_for(b.n_reads, 256, 16), 256, 0, s>>>(b.d_offsets, b.n_reads, K, b.d_flags, d_kcount, d_status, d_tot); ++g_launches;
         CU(cudaGetLastError());
     }
     CU(cudaMemcpyAsync(g_ctx.h_scratch, d_tot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -655,6 +720,16 @@ extern "C" int64_t gt_insert_batch(gt_storage* st, int shifter, int K, gt_batch*
     int64_t n = gt_batch_n_kmers(b, K);
     if (n < 0) return -1;
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : g_ctx.main;
+    if (bucket_usable(st, mode, K, (uint64_t)n, (uint64_t)n)) {
+        // K1b runs on the compute stream, ordered after what the caller queued on `stream`
+        if (s != g_ctx.main) {
+            CU(cudaEventRecord(g_ctx.slot[0].packed, s));
+            CU(cudaStreamWaitEvent(g_ctx.main, g_ctx.slot[0].packed, 0));
+        }
+        if (bucket_insert(st, shifter, *b, K, (uint64_t)n)) return -1;
+        return n;
+    }
+    if (mode != GT_MODE_BLIND && pending_flush_sync(st)) return -1;
     if (launch_insert(st, shifter, *b, K, mode, nullptr, s)) return -1;
     return n;
 }
@@ -671,8 +746,23 @@ extern "C" int64_t gt_insert_sequences(gt_storage* st, int shifter, int K, const
     if (validate_offsets("gt_insert_sequences", offsets, n_reads)) return -1;
     if (n_reads == 0) return 0;
     CU(cudaSetDevice(g_ctx.device));
+    if (mode != GT_MODE_BLIND && pending_flush_sync(st)) return -1;  // is_new must see every earlier insert
     std::vector<uint64_t> cuts;
     chunk_ranges(offsets, n_reads, cuts);
+    // host-side upper bound of each chunk's k-mers (invalid reads only lower it)
+    std::vector<uint64_t> chunk_kmers(cuts.size() - 1, 0);
+    uint64_t call_kmers = 0, max_chunk = 0;
+    for (size_t c = 0; c + 1 < cuts.size(); ++c) {
+        uint64_t k = 0;
+        for (uint64_t r = cuts[c]; r < cuts[c + 1]; ++r) {
+            uint64_t len = offsets[r + 1] - offsets[r];
+            if (len >= (uint64_t)K) k += len - K + 1;
+        }
+        chunk_kmers[c] = k;
+        call_kmers += k;
+        max_chunk = std::max(max_chunk, k);
+    }
+    const bool bucketed = !n_new_per_read && bucket_usable(st, mode, K, max_chunk, call_kmers);
     // k-mer total accumulates on the device across chunks (scratch[3]); read once at the end
     unsigned long long* d_tot = g_ctx.d_scratch + 3;
     CU(cudaMemsetAsync(d_tot, 0, sizeof(unsigned long long), g_ctx.slot[0].stream));
@@ -682,13 +772,17 @@ extern "C" int64_t gt_insert_sequences(gt_storage* st, int shifter, int K, const
         cudaStream_t s = sl.stream;
         uint64_t r0 = cuts[c], r1 = cuts[c + 1], nr = r1 - r0;
         gt_batch view;
+        if (sl.consumed_pending) {  // the compute stream may still be reading this slot's buffers
+            CU(cudaStreamWaitEvent(s, sl.consumed, 0));
+            sl.consumed_pending = false;
+        }
         if (stage_chunk(sl, bases, offsets, r0, r1, view)) return -1;
         uint8_t* d_status = nullptr;
         if (status) {
             if (sl.out8.reserve(nr, s)) return -1;
             d_status = sl.out8.as<uint8_t>();
         }
-        k_kmer_counts<<<grid_for(nr, 256, 16), 256, 0, s>>>(view.d_offsets, nr, K, view.d_flags, nullptr, d_status, d_tot);
+        k_kmer_counts<<<grid_for(nr, 256, 16), 256, 0, s>>>(view.d_offsets, nr, K, view.d_flags, nullptr, d_status, d_tot); ++g_launches;
         CU(cudaGetLastError());
         uint64_t* d_n_new = nullptr;
         if (n_new_per_read) {
@@ -696,14 +790,154 @@ extern "C" int64_t gt_insert_sequences(gt_storage* st, int shifter, int K, const
             d_n_new = sl.out64a.as<uint64_t>();
             CU(cudaMemsetAsync(d_n_new, 0, nr * 8, s));
         }
-        if (launch_insert(st, shifter, view, K, mode, d_n_new, s)) return -1;
+        if (bucketed) {
+            // copies + pack ran on the slot stream; hashing/bucketing runs on the compute stream
+            CU(cudaEventRecord(sl.packed, s));
+            CU(cudaStreamWaitEvent(g_ctx.main, sl.packed, 0));
+            if (bucket_insert(st, shifter, view, K, chunk_kmers[c])) return -1;
+            CU(cudaEventRecord(sl.consumed, g_ctx.main));
+            sl.consumed_pending = true;
+        } else if (launch_insert(st, shifter, view, K, mode, d_n_new, s)) {
+            return -1;
+        }
         if (status) CU(cudaMemcpyAsync(status + r0, d_status, nr, cudaMemcpyDeviceToHost, s));
         if (n_new_per_read) CU(cudaMemcpyAsync(n_new_per_read + r0, d_n_new, nr * 8, cudaMemcpyDeviceToHost, s));
     }
     CU(cudaStreamSynchronize(g_ctx.slot[0].stream));
     CU(cudaStreamSynchronize(g_ctx.slot[1].stream));
+    if (bucketed) {
+        CU(cudaStreamSynchronize(g_ctx.main));
+        g_ctx.slot[0].consumed_pending = g_ctx.slot[1].consumed_pending = false;
+    }
     CU(cudaMemcpy(g_ctx.h_scratch + 3, d_tot, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return (int64_t)g_ctx.h_scratch[3];
+}
+
+// Same walk, reads already in HBM as ASCII (d_bases) with device offsets starting at 0.
+extern "C" int64_t gt_insert_sequences_dev(gt_storage* st, int shifter, int K, const void* d_bases, const void* d_offsets,
+                                            uint64_t n_reads, uint64_t n_bases, int mode) {
+    if (ensure_ctx()) return -1;
+    if (!st) return fail("gt_insert_sequences_dev: NULL storage");
+    if (K < 1 || K > 65535) return fail("gt_insert_sequences_dev: K=%d out of range (1..65535)", K);
+    if (check_mode("gt_insert_sequences_dev", mode)) return -1;
+    if (n_reads >= (1ull << 32)) return fail("gt_insert_sequences_dev: more than 2^32-1 reads in one call");
+    if (n_reads == 0) return 0;
+    if (!d_bases || !d_offsets) return fail("gt_insert_sequences_dev: NULL device pointer");
+    CU(cudaSetDevice(g_ctx.device));
+    if (mode != GT_MODE_BLIND && pending_flush_sync(st)) return -1;
+    // pack into slot 0's buffers on the compute stream (everything here is stream-ordered on it)
+    Slot& sl = g_ctx.slot[0];
+    cudaStream_t s = g_ctx.main;
+    if (sl.consumed_pending) {
+        CU(cudaStreamWaitEvent(s, sl.consumed, 0));
+        sl.consumed_pending = false;
+    }
+    CU(cudaStreamSynchronize(sl.stream));
+    uint64_t n_words = (n_bases + 31) / 32, n_words_alloc = n_words + halo_alloc_words();
+    if (sl.words.reserve(n_words_alloc * 8, s) || sl.flags.reserve(n_reads + 1, s) ||
+        sl.coarse.reserve(((n_bases >> COARSE_SHIFT) + 2) * 4, s))
+        return -1;
+    const uint64_t* offs = static_cast<const uint64_t*>(d_offsets);
+    if (pack_on_device(static_cast<const uint8_t*>(d_bases), offs, n_reads, n_bases, 0, sl.words.as<uint64_t>(), n_words_alloc,
+                       sl.flags.as<uint8_t>(), sl.coarse.as<uint32_t>(), s))
+        return -1;
+    gt_batch view;
+    view.n_reads = n_reads;
+    view.n_bases = n_bases;
+    view.n_words = n_words;
+    view.n_words_alloc = n_words_alloc;
+    view.base0 = 0;
+    view.d_words = sl.words.as<uint64_t>();
+    view.d_offsets = const_cast<uint64_t*>(offs);
+    view.d_flags = sl.flags.as<uint8_t>();
+    view.d_coarse = sl.coarse.as<uint32_t>();
+    unsigned long long* d_tot = g_ctx.d_scratch + 3;
+    CU(cudaMemsetAsync(d_tot, 0, sizeof(unsigned long long), s));
+    k_kmer_counts<<<grid_for(n_reads, 256, 16), 256, 0, s>>>(offs, n_reads, K, view.d_flags, nullptr, nullptr, d_tot); ++g_launches;
+    CU(cudaGetLastError());
+    // n_bases bounds the k-mers of the batch without a round trip to the host
+    if (bucket_usable(st, mode, K, n_bases, n_bases)) {
+        if (bucket_insert(st, shifter, view, K, n_bases)) return -1;
+    } else if (launch_insert(st, shifter, view, K, mode, nullptr, s)) {
+        return -1;
+    }
+    CU(cudaMemcpyAsync(g_ctx.h_scratch + 3, d_tot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return (int64_t)g_ctx.h_scratch[3];
+}
+
+// Apply every pending (write-combined) insert of `st` to its tables and wait for it.
+extern "C" int gt_storage_flush(gt_storage* st) {
+    if (ensure_ctx()) return -1;
+    if (!st) return fail("gt_storage_flush: NULL storage");
+    if (pending_flush_sync(st)) return -1;
+    return 0;
+}
+
+extern "C" int gt_storage_pending_info(gt_storage* st, uint64_t* info) {
+    if (ensure_ctx()) return -1;
+    if (!st || !info) return fail("gt_storage_pending_info: NULL argument");
+    memset(info, 0, 8 * sizeof(uint64_t));
+    if (!st->pend) return 0;
+    Pending* p = st->pend;
+    unsigned long long nd = 0;
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(&nd, p->d_n_direct, 8, cudaMemcpyDeviceToHost));
+    info[0] = 1;
+    info[1] = (uint64_t)p->n_buckets;
+    info[2] = (uint64_t)p->plan.shift;
+    info[3] = p->budget_kmers;
+    info[4] = p->entries_total;
+    info[5] = p->pending_kmers;
+    info[6] = nd;
+    info[7] = p->total_chunks;
+    return 0;
+}
+
+extern "C" uint64_t gt_launch_count(void) { return g_launches; }
+
+// Device timing helpers for harnesses: events recorded on the library's compute stream.
+static cudaEvent_t g_timer[8] = {nullptr};
+extern "C" int gt_timer_record(int slot) {
+    if (ensure_ctx()) return -1;
+    if (slot < 0 || slot >= 8) return fail("gt_timer_record: slot 0..7");
+    if (!g_timer[slot]) CU(cudaEventCreate(&g_timer[slot]));
+    // the compute stream is ordered after both staging streams at this point
+    for (auto& sl : g_ctx.slot) {
+        CU(cudaEventRecord(sl.packed, sl.stream));
+        CU(cudaStreamWaitEvent(g_ctx.main, sl.packed, 0));
+    }
+    CU(cudaEventRecord(g_timer[slot], g_ctx.main));
+    return 0;
+}
+extern "C" double gt_timer_elapsed_ms(int from_slot, int to_slot) {
+    if (ensure_ctx()) return -1.0;
+    if (from_slot < 0 || from_slot >= 8 || to_slot < 0 || to_slot >= 8 || !g_timer[from_slot] || !g_timer[to_slot]) {
+        fail("gt_timer_elapsed_ms: slots not recorded");
+        return -1.0;
+    }
+    float ms = 0;
+    if (cudaEventSynchronize(g_timer[to_slot]) != cudaSuccess || cudaEventElapsedTime(&ms, g_timer[from_slot], g_timer[to_slot]) != cudaSuccess) {
+        fail("gt_timer_elapsed_ms: %s", cudaGetErrorString(cudaGetLastError()));
+        return -1.0;
+    }
+    return (double)ms;
+}
+extern "C" int gt_profile_enable(int on) {
+    if (ensure_ctx()) return -1;
+    CU(cudaDeviceSynchronize());
+    prof_resolve();
+    g_prof_on = on != 0;
+    for (int k = 0; k < PROF_KINDS; ++k) { g_prof_ms[k] = 0; g_prof_n[k] = 0; }
+    return 0;
+}
+extern "C" int gt_profile_get(double* ms3, uint64_t* n3) {
+    if (ensure_ctx()) return -1;
+    if (!ms3 || !n3) return fail("gt_profile_get: NULL argument");
+    CU(cudaDeviceSynchronize());
+    prof_resolve();
+    for (int k = 0; k < PROF_KINDS; ++k) { ms3[k] = g_prof_ms[k]; n3[k] = g_prof_n[k]; }
+    return 0;
 }
 
 // exclusive scan of per-read k-mer counts on stream s
@@ -712,9 +946,9 @@ static int scan_counts(Slot& sl, const uint64_t* d_in, uint64_t n, uint64_t* d_o
     uint64_t per = (uint64_t)SCAN_BLOCK * SCAN_ITEMS;
     uint64_t nb = (n + per - 1) / per;
     if (sl.partial.reserve(nb * 8, s)) return -1;
-    k_scan_partials<<<(unsigned)nb, SCAN_BLOCK, 0, s>>>(d_in, n, sl.partial.as<uint64_t>());
-    k_scan_top<<<1, 1024, 0, s>>>(sl.partial.as<uint64_t>(), nb);
-    k_scan_final<<<(unsigned)nb, SCAN_BLOCK, 0, s>>>(d_in, n, sl.partial.as<uint64_t>(), d_out);
+    k_scan_partials<<<(unsigned)nb, SCAN_BLOCK, 0, s>>>(d_in, n, sl.partial.as<uint64_t>()); ++g_launches;
+    k_scan_top<<<1, 1024, 0, s>>>(sl.partial.as<uint64_t>(), nb); ++g_launches;
+    k_scan_final<<<(unsigned)nb, SCAN_BLOCK, 0, s>>>(d_in, n, sl.partial.as<uint64_t>(), d_out); ++g_launches;
     CU(cudaGetLastError());
     return 0;
 }
@@ -768,6 +1002,7 @@ extern "C" int64_t gt_query_sequences(gt_storage* st, int shifter, int K, const 
                                        uint64_t n_reads, int16_t* counts, uint8_t* status) {
     if (check_reads("gt_query_sequences", bases, offsets, n_reads, K)) return -1;
     if (!st || !counts) return fail("gt_query_sequences: NULL argument");
+    if (pending_flush_sync(st)) return -1;
     if (validate_offsets("gt_query_sequences", offsets, n_reads)) return -1;
     if (n_reads == 0) return 0;
     CU(cudaSetDevice(g_ctx.device));
@@ -788,6 +1023,7 @@ extern "C" int64_t gt_median_count_at_least(gt_storage* st, int shifter, int K, 
                                              uint64_t n_reads, uint32_t cutoff, uint8_t* pass, uint8_t* status) {
     if (check_reads("gt_median_count_at_least", bases, offsets, n_reads, K)) return -1;
     if (!st || !pass) return fail("gt_median_count_at_least: NULL argument");
+    if (pending_flush_sync(st)) return -1;
     if (validate_offsets("gt_median_count_at_least", offsets, n_reads)) return -1;
     if (n_reads == 0) return 0;
     CU(cudaSetDevice(g_ctx.device));
@@ -805,14 +1041,14 @@ extern "C" int64_t gt_median_count_at_least(gt_storage* st, int shifter, int K, 
         if (sl.kcount.reserve(nr * 8, s) || sl.hits.reserve(nr * 4, s) || sl.out8.reserve(2 * nr, s)) return -1;
         uint8_t* d_status = sl.out8.as<uint8_t>();
         uint8_t* d_pass = d_status + nr;
-        k_kmer_counts<<<grid_for(nr, 256, 16), 256, 0, s>>>(view.d_offsets, nr, K, view.d_flags, sl.kcount.as<uint64_t>(), d_status, d_tot);
+        k_kmer_counts<<<grid_for(nr, 256, 16), 256, 0, s>>>(view.d_offsets, nr, K, view.d_flags, sl.kcount.as<uint64_t>(), d_status, d_tot); ++g_launches;
         CU(cudaGetLastError());
         CU(cudaMemsetAsync(sl.hits.p, 0, nr * 4, s));
         WalkArgs a = make_args(view, K);
         a.hits = sl.hits.as<uint32_t>();
         a.cutoff = cutoff;
         if (launch_walk_kind<OP_MEDIAN, false>(shifter, a, st->ts, s)) return -1;
-        k_median_decide<<<grid_for(nr, 256, 16), 256, 0, s>>>(sl.kcount.as<uint64_t>(), a.hits, nr, d_pass);
+        k_median_decide<<<grid_for(nr, 256, 16), 256, 0, s>>>(sl.kcount.as<uint64_t>(), a.hits, nr, d_pass); ++g_launches;
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(pass + r0, d_pass, nr, cudaMemcpyDeviceToHost, s));
         if (status) CU(cudaMemcpyAsync(status + r0, d_status, nr, cudaMemcpyDeviceToHost, s));
@@ -830,7 +1066,7 @@ template <int KIND, bool TRACK>
 static void launch_insert_hashes_t(const gt_storage* st, const uint64_t* d_h, uint64_t n, uint8_t* d_new, cudaStream_t s) {
     int grid = grid_for(n, 256 * 4, 8);
     if (st->n == 4) k_insert_hashes<KIND, TRACK, 4><<<grid, 256, 0, s>>>(d_h, n, st->ts, d_new, st->d_n_unique);
-    else k_insert_hashes<KIND, TRACK, 0><<<grid, 256, 0, s>>>(d_h, n, st->ts, d_new, st->d_n_unique);
+    else k_insert_hashes<KIND, TRACK, 0><<<grid, 256, 0, s>>>(d_h, n, st->ts, d_new, st->d_n_unique); ++g_launches;
 }
 
 extern "C" int gt_insert_hashes(gt_storage* st, const uint64_t* hashes, uint64_t n, int mode, uint8_t* is_new) {
@@ -838,6 +1074,7 @@ extern "C" int gt_insert_hashes(gt_storage* st, const uint64_t* hashes, uint64_t
     if (!st || (n && !hashes)) return fail("gt_insert_hashes: NULL argument");
     if (check_mode("gt_insert_hashes", mode)) return -1;
     if (is_new && mode == GT_MODE_BLIND) return fail("gt_insert_hashes: is_new needs GT_MODE_FAST or GT_MODE_EXACT");
+    if (mode != GT_MODE_BLIND && pending_flush_sync(st)) return -1;  // is_new must see every earlier insert
     if (n == 0) return 0;
     CU(cudaSetDevice(g_ctx.device));
     const uint64_t chunk = 64ull << 20;  // hashes per chunk
@@ -869,6 +1106,7 @@ extern "C" int gt_insert_hashes(gt_storage* st, const uint64_t* hashes, uint64_t
 extern "C" int gt_query_hashes(gt_storage* st, const uint64_t* hashes, uint64_t n, int16_t* counts) {
     if (ensure_ctx()) return -1;
     if (!st || (n && (!hashes || !counts))) return fail("gt_query_hashes: NULL argument");
+    if (pending_flush_sync(st)) return -1;
     if (n == 0) return 0;
     CU(cudaSetDevice(g_ctx.device));
     const uint64_t chunk = 64ull << 20;
@@ -884,11 +1122,11 @@ extern "C" int gt_query_hashes(gt_storage* st, const uint64_t* hashes, uint64_t 
         if (st->n == 4) {
             if (st->kind == 0) k_query_hashes<0, 4><<<grid, 256, 0, s>>>(d_h, m, st->ts, d_c);
             else if (st->kind == 1) k_query_hashes<1, 4><<<grid, 256, 0, s>>>(d_h, m, st->ts, d_c);
-            else k_query_hashes<2, 4><<<grid, 256, 0, s>>>(d_h, m, st->ts, d_c);
+            else k_query_hashes<2, 4><<<grid, 256, 0, s>>>(d_h, m, st->ts, d_c); ++g_launches;
         } else {
             if (st->kind == 0) k_query_hashes<0, 0><<<grid, 256, 0, s>>>(d_h, m, st->ts, d_c);
             else if (st->kind == 1) k_query_hashes<1, 0><<<grid, 256, 0, s>>>(d_h, m, st->ts, d_c);
-            else k_query_hashes<2, 0><<<grid, 256, 0, s>>>(d_h, m, st->ts, d_c);
+            else k_query_hashes<2, 0><<<grid, 256, 0, s>>>(d_h, m, st->ts, d_c); ++g_launches;
         }
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(counts + i0, d_c, m * 2, cudaMemcpyDeviceToHost, s));

@@ -150,6 +150,17 @@ class dBG:
             out.append(status[:n])
         return out[0] if len(out) == 1 else tuple(out)
 
+    def insert_sequences_dev(self, d_bases_ptr, d_offsets_ptr, n_reads, n_bases, mode=None):
+        """Same as insert_sequences for ASCII bases + uint64 offsets already resident in HBM
+        (raw device pointers, e.g. torch tensors' data_ptr())."""
+        mode = self.mode if mode is None else mode
+        return int(_capi.check(_capi.lib().gt_insert_sequences_dev(self.S.handle, self.hasher.shifter_kind, self.K,
+                                                                   d_bases_ptr, d_offsets_ptr, n_reads, n_bases,
+                                                                   mode), "gt_insert_sequences_dev"))
+
+    def flush(self):
+        self.S.flush()
+
     def query_sequences(self, bases, offsets, want_status=False):
         """dBG::query_sequence over a read batch: counts of all k-mers, reads back to back."""
         L = _capi.lib()

@@ -131,6 +131,17 @@ class _Storage:
     def reset(self):
         _capi.check(_capi.lib().gt_storage_reset(self._h), "gt_storage_reset")
 
+    def flush(self):
+        """Apply every pending write-combined blind insert (include/goetia_b200.h, gt_storage_flush)."""
+        _capi.check(_capi.lib().gt_storage_flush(self._h), "gt_storage_flush")
+
+    def pending_info(self):
+        a = np.zeros(8, dtype=np.uint64)
+        _capi.check(_capi.lib().gt_storage_pending_info(self._h, a.ctypes.data), "gt_storage_pending_info")
+        keys = ("built", "n_buckets", "slice_shift", "budget_kmers", "entries", "pending_kmers", "n_direct",
+                "apply_grid")
+        return dict(zip(keys, (int(v) for v in a)))
+
     # -- single-hash members (one launch each; the batch members are the fast path) ---------
     def insert(self, khash, mode=_capi.MODE_FAST):
         return bool(self.insert_many([_hash_value(khash)], mode=mode)[0])

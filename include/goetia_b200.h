@@ -154,6 +154,35 @@ int gt_batch_status(gt_batch* b, int K, uint8_t* status);
 /* Queue insert / query of a resident batch on `stream` (0 = library stream); asynchronous. */
 int64_t gt_insert_batch(gt_storage* st, int shifter, int K, gt_batch* b, int mode, void* stream);
 
+/* dBG::insert_sequence over a batch whose ASCII bases and offsets (uint64, offsets[0] == 0) are
+ * already resident in HBM.  Queues pack + hash + insert on the library's compute stream and
+ * returns the k-mers consumed (one 8-byte read-back). */
+int64_t gt_insert_sequences_dev(gt_storage* st, int shifter, int K, const void* d_bases,
+                                const void* d_offsets, uint64_t n_reads, uint64_t n_bases, int mode);
+
+/* ---- write-combining of blind inserts --------------------------------------------------- */
+/* GT_MODE_BLIND inserts into tables larger than L2 are not applied one by one: each update
+ * is appended to the bucket of its table slice and applied slice by slice (DESIGN.md,
+ * "write-combining insert").  Every call that reads a table (query, stats, download, save,
+ * update_from, tracked inserts) applies what is pending first, so the semantics of
+ * Storage::insert (bitstorage.hh:195-219 etc.) are unchanged; gt_storage_flush forces it. */
+int gt_storage_flush(gt_storage* st);
+/* diagnostics: info[8] = {store built, n_buckets, log2(slots per slice), k-mer budget between
+ * flushes, entries allocated, pending k-mers (upper bound), updates that overflowed a bucket
+ * and were applied directly, apply-grid size} */
+int gt_storage_pending_info(gt_storage* st, uint64_t* info);
+/* number of CUDA kernels this library has launched so far in this process */
+uint64_t gt_launch_count(void);
+/* Device timing for harnesses (the library launches on its own streams, which events of
+ * another runtime's stream do not see).  gt_timer_record puts a CUDA event on the compute
+ * stream (ordered after everything queued so far); gt_timer_elapsed_ms waits for both. */
+int gt_timer_record(int slot);                       /* slot 0..7 */
+double gt_timer_elapsed_ms(int from_slot, int to_slot);
+/* Per-kernel device time of the insert kernels, from CUDA event pairs around each launch:
+ * ms3/n3 = {k_bucket, k_apply, k_walk} accumulated since gt_profile_enable(1). */
+int gt_profile_enable(int on);
+int gt_profile_get(double* ms3, uint64_t* n3);
+
 /* ---- SourmashSketch (sketches/sourmash_sketch.hh:24-82) -------------------------------- */
 /* Sketch(n, K, is_protein=false, dayhoff=false, hp=false, seed, scaled):
  * max_hash_from_scaled (:52-61) is applied by the caller via gt_max_hash_from_scaled. */
