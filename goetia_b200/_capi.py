@@ -63,6 +63,13 @@ SIGNATURES = {
                                             C.c_uint64, C.c_int]),
     "gt_storage_flush": (C.c_int, [C.c_void_p]),
     "gt_storage_pending_info": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gt_storage_apply": (C.c_int, [C.c_void_p]),
+    "gt_shard_plan": (C.c_int, [C.c_int, u64p, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gt_storage_create_sharded": (C.c_void_p, [C.c_int, u64p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int]),
+    "gt_storage_local_range": (C.c_int, [C.c_void_p, C.c_int, u64p, u64p]),
+    "gt_storage_attach_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gt_set_compute_stream": (C.c_int, [C.c_void_p]),
     "gt_launch_count": (C.c_uint64, []),
     "gt_timer_record": (C.c_int, [C.c_int]),
     "gt_timer_elapsed_ms": (C.c_double, [C.c_int, C.c_int]),

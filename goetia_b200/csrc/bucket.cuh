@@ -18,7 +18,7 @@
 //   K1b k_bucket      : stage packed tile -> roll both cyclic hashes -> n_tables fastmods ->
 //                       CTA-local counting sort by slice in shared memory -> one global
 //                       cursor reservation per (tile, slice) -> coalesced run copies.
-//   K2  k_apply       : CTA = one 4096-entry chunk of one bucket, buckets in blockIdx order;
+//   K2  k_apply       : CTA = one 4096-entry chunk of one bucket, buckets in blockIdx (= slice) order;
 //                       16 B streaming loads of entries, RED.OR / CAS into the slice.
 #pragma once
 #include <cuda_runtime.h>
@@ -33,15 +33,31 @@ constexpr int AP_THREADS = 256;
 constexpr int AP_PER_THREAD = 16;
 constexpr int AP_CHUNK = AP_THREADS * AP_PER_THREAD;  // entries per apply CTA
 
-struct BucketPlan {
+// What k_bucket needs: where each bucket's entries go.  With one GPU every bucket lives in the
+// storage's own pending store; in a sharded storage (one process per GPU, table t cut into
+// per-rank slot ranges) the buckets of slices owned by a peer point into that peer's outbox
+// region (or straight into peer memory), and own_lo/own_hi give this rank's slot range.
+struct ProducePlan {
     int n_tables;
     int shift;                        // log2(slots per slice)
-    int n_buckets;                    // all tables
+    int n_buckets;                    // all tables, all owners
     uint32_t first[MAX_TABLES + 1];   // first bucket id of table t
-    uint32_t* const* bptr;            // [n_buckets] entry array of each bucket (may be peer memory)
+    uint64_t own_lo[MAX_TABLES];      // slots [own_lo, own_hi) of table t are held by this rank
+    uint64_t own_hi[MAX_TABLES];
+    uint32_t* const* bptr;            // [n_buckets] entry array of each bucket
     const uint32_t* bcap;             // [n_buckets] capacity in entries
-    uint32_t* bfill;                  // [n_buckets] cursor; can exceed bcap (excess was applied directly)
-    unsigned long long* n_direct;     // diagnostics: updates that overflowed a bucket
+    uint32_t* bfill;                  // [n_buckets] cursor; can exceed bcap (excess handled at once)
+    unsigned long long* n_direct;     // updates that overflowed a bucket and were applied directly
+    unsigned long long* n_dropped;    // overflowed updates of slots this rank does not hold (an error)
+};
+
+// What k_apply walks: one item per (slice, source rank) in slice order.
+struct ApplyItem {
+    const uint32_t* src;   // entries
+    const uint32_t* fill;  // device location of the entry count (a cursor, or a received count)
+    uint64_t slot0;        // first slot of the slice in table coordinates
+    uint32_t cap;
+    uint32_t table;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -49,7 +65,7 @@ struct BucketPlan {
 // ------------------------------------------------------------------------------------------
 template <int KIND, bool CAN, int NT>
 __global__ void __launch_bounds__(TILE_THREADS, 2)
-k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts, const __grid_constant__ BucketPlan bp) {
+k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts, const __grid_constant__ ProducePlan bp) {
     extern __shared__ __align__(16) uint64_t smem[];
     const int K = a.K;
     const int halo_words = ((K - 1 + 31) >> 5) + 1;
@@ -70,7 +86,7 @@ k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts
     }
     const uint64_t n_tiles = (a.n_bases + TILE_POS - 1) / TILE_POS;
     const uint64_t slot_mask = (1ull << bp.shift) - 1;
-    unsigned long long direct = 0;
+    unsigned long long direct = 0, dropped = 0;
 
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         __syncthreads();  // previous tile fully flushed; tab visible
@@ -200,8 +216,13 @@ k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts
                     if (g + e < cap) {
                         dst[g + e] = off;
                     } else {  // bucket full (skewed input): apply here, correctness never depends on capacity
-                        slot_insert<KIND, false>(ts.ptr[t], ((uint64_t)(b - fb) << bp.shift) + off);
-                        ++direct;
+                        const uint64_t bin = ((uint64_t)(b - fb) << bp.shift) + off;
+                        if (bin >= bp.own_lo[t] && bin < bp.own_hi[t]) {
+                            slot_insert<KIND, false>(ts.ptr[t], bin);
+                            ++direct;
+                        } else {
+                            ++dropped;
+                        }
                     }
                 }
             }
@@ -209,6 +230,7 @@ k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts
         }
     }
     if (direct) atomicAdd(bp.n_direct, direct);
+    if (dropped) atomicAdd(bp.n_dropped, dropped);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -218,11 +240,12 @@ k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts
 // grid needs no device-side planning; CTAs past a bucket's fill exit at once.
 template <int KIND>
 __global__ void __launch_bounds__(AP_THREADS)
-k_apply(const __grid_constant__ TableSet ts, const __grid_constant__ BucketPlan bp, const uint32_t* __restrict__ chunk_start) {
+k_apply(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ items, const uint32_t* __restrict__ chunk_start,
+        int n_items) {
     __shared__ uint32_t s_b;
     if (threadIdx.x == 0) {
-        // bucket of this CTA: largest b with chunk_start[b] <= blockIdx.x
-        uint32_t lo = 0, hi = (uint32_t)bp.n_buckets;
+        // item of this CTA: largest b with chunk_start[b] <= blockIdx.x
+        uint32_t lo = 0, hi = (uint32_t)n_items;
         while (hi - lo > 1) {
             uint32_t mid = (lo + hi) >> 1;
             if (__ldg(chunk_start + mid) <= blockIdx.x) lo = mid; else hi = mid;
@@ -231,15 +254,12 @@ k_apply(const __grid_constant__ TableSet ts, const __grid_constant__ BucketPlan 
     }
     __syncthreads();
     const uint32_t b = s_b;
-    const uint32_t fill = min(__ldcg(bp.bfill + b), __ldg(bp.bcap + b));
+    const ApplyItem it = items[b];
+    const uint32_t fill = min(__ldcg(it.fill), it.cap);
     const uint32_t e0 = (blockIdx.x - __ldg(chunk_start + b)) * (uint32_t)AP_CHUNK;
     if (e0 >= fill) return;
-    int t = 0;
-    while (b >= bp.first[t + 1]) ++t;
-    // slice base: slice index * 2^shift slots -> words
-    const uint64_t slot0 = (uint64_t)(b - bp.first[t]) << bp.shift;
-    uint32_t* tbl = ts.ptr[t] + (KIND == 0 ? (slot0 >> 5) : KIND == 1 ? (slot0 >> 2) : (slot0 >> 3));
-    const uint32_t* src = bp.bptr[b];
+    uint32_t* tbl = ts.ptr[it.table] + (KIND == 0 ? (it.slot0 >> 5) : KIND == 1 ? (it.slot0 >> 2) : (it.slot0 >> 3));
+    const uint32_t* src = it.src;
     const uint32_t n = min((uint32_t)AP_CHUNK, fill - e0);
     // 16 B streaming loads where the chunk is full and aligned; scalar tail otherwise
     if (n == AP_CHUNK && ((reinterpret_cast<uintptr_t>(src + e0) & 15) == 0)) {

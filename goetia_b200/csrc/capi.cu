@@ -92,7 +92,8 @@ struct Context {
     bool ready = false;
     int device = -1;
     int sms = 0;
-    cudaStream_t main = nullptr;
+    cudaStream_t main = nullptr;      // compute stream (the library's own unless gt_set_compute_stream gave another)
+    cudaStream_t own_main = nullptr;
     Slot slot[2];
     unsigned long long* d_scratch = nullptr;  // [0] k-mer total, [1] occupied, [2..7] spare
     unsigned long long* h_scratch = nullptr;  // pinned mirror
@@ -180,7 +181,8 @@ extern "C" int gt_init(int device) {
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail("gt_init: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     g_ctx.sms = prop.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&g_ctx.main, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&g_ctx.own_main, cudaStreamNonBlocking));
+    g_ctx.main = g_ctx.own_main;
     for (auto& s : g_ctx.slot) {
         CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&s.packed, cudaEventDisableTiming));
@@ -241,15 +243,33 @@ struct gt_storage {
     uint64_t sizes[MAX_TABLES];
     uint64_t ref_bytes[MAX_TABLES];    // bytes the reference allocates
     uint64_t alloc_bytes[MAX_TABLES];  // bytes we allocate (multiple of 16, >= ref_bytes)
-    TableSet ts;
+    TableSet ts;                       // ts.ptr[i] is indexed by GLOBAL slot (biased by own_lo in a sharded storage)
     unsigned long long* d_n_unique = nullptr;
+    // sharding (one process per GPU): this rank holds slots [own_lo, own_hi) of table i in slab[i]
+    int rank = 0, world = 1;
+    uint64_t own_lo[MAX_TABLES], own_hi[MAX_TABLES];
+    void* slab[MAX_TABLES];
 };
 
 static uint64_t ref_table_bytes(int kind, uint64_t size) {
     return kind == GT_STORAGE_BIT ? size / 8 + 1 : kind == GT_STORAGE_BYTE ? size : size / 2 + 1;
 }
 
-extern "C" gt_storage* gt_storage_create(int kind, const uint64_t* tablesizes, int n_tables) {
+// bytes of the slots [lo, hi) of a table (lo is a multiple of the slice size, so of 8 and 2)
+static uint64_t range_bytes(int kind, uint64_t lo, uint64_t hi, bool last) {
+    if (hi <= lo) return 0;
+    uint64_t n = hi - lo;
+    if (kind == GT_STORAGE_BIT) return last ? hi / 8 + 1 - lo / 8 : n / 8;
+    if (kind == GT_STORAGE_BYTE) return n;
+    return last ? hi / 2 + 1 - lo / 2 : n / 2;
+}
+static int slots_per_word(int kind) { return kind == GT_STORAGE_BIT ? 32 : kind == GT_STORAGE_BYTE ? 4 : 8; }
+
+struct PlanHost;
+static int make_plan(int kind, const uint64_t* sizes, int n, int world, uint64_t budget, int slice_log2_bytes, PlanHost& P);
+
+static gt_storage* storage_create(int kind, const uint64_t* tablesizes, int n_tables, int rank, int world,
+                                  const uint64_t* own_lo, const uint64_t* own_hi) {
     if (ensure_ctx()) return nullptr;
     if (kind < 0 || kind > 2) { fail("gt_storage_create: unknown storage kind %d", kind); return nullptr; }
     if (!tablesizes || n_tables < 1 || n_tables > MAX_TABLES) {
@@ -260,7 +280,10 @@ extern "C" gt_storage* gt_storage_create(int kind, const uint64_t* tablesizes, i
     gt_storage* st = new gt_storage();
     st->kind = kind;
     st->n = n_tables;
+    st->rank = rank;
+    st->world = world;
     memset(&st->ts, 0, sizeof st->ts);
+    memset(st->slab, 0, sizeof st->slab);
     st->ts.n = n_tables;
     st->ts.kind = kind;
     for (int i = 0; i < n_tables; ++i) {
@@ -271,8 +294,11 @@ extern "C" gt_storage* gt_storage_create(int kind, const uint64_t* tablesizes, i
             return nullptr;
         }
         st->sizes[i] = d;
-        st->ref_bytes[i] = ref_table_bytes(kind, d);
-        st->alloc_bytes[i] = (st->ref_bytes[i] + 15) / 16 * 16;
+        st->own_lo[i] = own_lo ? own_lo[i] : 0;
+        st->own_hi[i] = own_hi ? own_hi[i] : d;
+        // bytes of the part held here, laid out exactly as the reference lays out that part of its table
+        st->ref_bytes[i] = world == 1 ? ref_table_bytes(kind, d) : range_bytes(kind, st->own_lo[i], st->own_hi[i], st->own_hi[i] == d);
+        st->alloc_bytes[i] = (st->ref_bytes[i] + 15) / 16 * 16 + 16;
         st->ts.size[i] = d;
         st->ts.magic[i] = ~0ull / d;
         void* p = nullptr;
@@ -282,7 +308,10 @@ extern "C" gt_storage* gt_storage_create(int kind, const uint64_t* tablesizes, i
             gt_storage_destroy(st);
             return nullptr;
         }
-        st->ts.ptr[i] = static_cast<uint32_t*>(p);
+        st->slab[i] = p;
+        // kernels index tables by global slot: bias the base by the first slot held here
+        st->ts.ptr[i] = reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(p) -
+                                                    (uintptr_t)(st->own_lo[i] / slots_per_word(kind)) * 4u);
     }
     if (cudaMalloc(&st->d_n_unique, sizeof(unsigned long long)) != cudaSuccess) {
         fail("gt_storage_create: cudaMalloc(counter) failed");
@@ -293,11 +322,15 @@ extern "C" gt_storage* gt_storage_create(int kind, const uint64_t* tablesizes, i
     return st;
 }
 
+extern "C" gt_storage* gt_storage_create(int kind, const uint64_t* tablesizes, int n_tables) {
+    return storage_create(kind, tablesizes, n_tables, 0, 1, nullptr, nullptr);
+}
+
 extern "C" void gt_storage_destroy(gt_storage* st) {
     if (!st) return;
     cudaDeviceSynchronize();
     for (int i = 0; i < st->n; ++i)
-        if (st->ts.ptr[i]) cudaFree(st->ts.ptr[i]);
+        if (st->slab[i]) cudaFree(st->slab[i]);
     if (st->d_n_unique) cudaFree(st->d_n_unique);
     pending_free(st->pend);
     delete st;
@@ -308,7 +341,7 @@ extern "C" int gt_storage_reset(gt_storage* st) {
     if (!st) return fail("gt_storage_reset: NULL storage");
     CU(cudaDeviceSynchronize());
     if (pending_discard(st)) return -1;
-    for (int i = 0; i < st->n; ++i) CU(cudaMemsetAsync(st->ts.ptr[i], 0, st->alloc_bytes[i], g_ctx.main));
+    for (int i = 0; i < st->n; ++i) CU(cudaMemsetAsync(st->slab[i], 0, st->alloc_bytes[i], g_ctx.main));
     CU(cudaMemsetAsync(st->d_n_unique, 0, sizeof(unsigned long long), g_ctx.main));
     CU(cudaStreamSynchronize(g_ctx.main));
     return 0;
@@ -328,7 +361,7 @@ extern "C" uint64_t gt_storage_table_bytes(const gt_storage* st, int i) {
 extern "C" void* gt_storage_device_table(gt_storage* st, int i) {
     if (!st || i < 0 || i >= st->n) return nullptr;
     if (pending_flush_sync(st)) return nullptr;
-    return st->ts.ptr[i];
+    return st->slab[i];
 }
 
 extern "C" int gt_storage_download_table(gt_storage* st, int i, uint8_t* host_dst) {
@@ -336,7 +369,7 @@ extern "C" int gt_storage_download_table(gt_storage* st, int i, uint8_t* host_ds
     if (!st || !host_dst || i < 0 || i >= st->n) return fail("gt_storage_download_table: bad argument");
     if (pending_flush_sync(st)) return -1;
     CU(cudaDeviceSynchronize());
-    CU(cudaMemcpy(host_dst, st->ts.ptr[i], st->ref_bytes[i], cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(host_dst, st->slab[i], st->ref_bytes[i], cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -345,8 +378,8 @@ extern "C" int gt_storage_upload_table(gt_storage* st, int i, const uint8_t* hos
     if (!st || !host_src || i < 0 || i >= st->n) return fail("gt_storage_upload_table: bad argument");
     if (pending_flush_sync(st)) return -1;
     CU(cudaDeviceSynchronize());
-    CU(cudaMemset(st->ts.ptr[i], 0, st->alloc_bytes[i]));
-    CU(cudaMemcpy(st->ts.ptr[i], host_src, st->ref_bytes[i], cudaMemcpyHostToDevice));
+    CU(cudaMemset(st->slab[i], 0, st->alloc_bytes[i]));
+    CU(cudaMemcpy(st->slab[i], host_src, st->ref_bytes[i], cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -368,9 +401,10 @@ extern "C" int gt_storage_stats(gt_storage* st, uint64_t* n_unique, uint64_t* n_
     // only the slots of the reference's table count; the padding words are always zero
     uint64_t n_words = st->alloc_bytes[0] / 4;
     int grid = grid_for(n_words, 256 * 8, 8);
-    if (st->kind == 0) k_count_occupied<0><<<grid, 256, 0, s>>>(st->ts.ptr[0], n_words, st->sizes[0], d_occ);
-    else if (st->kind == 1) k_count_occupied<1><<<grid, 256, 0, s>>>(st->ts.ptr[0], n_words, st->sizes[0], d_occ);
-    else k_count_occupied<2><<<grid, 256, 0, s>>>(st->ts.ptr[0], n_words, st->sizes[0], d_occ); ++g_launches;
+    const uint32_t* t0 = static_cast<const uint32_t*>(st->slab[0]);
+    if (st->kind == 0) k_count_occupied<0><<<grid, 256, 0, s>>>(t0, n_words, st->sizes[0], d_occ);
+    else if (st->kind == 1) k_count_occupied<1><<<grid, 256, 0, s>>>(t0, n_words, st->sizes[0], d_occ);
+    else k_count_occupied<2><<<grid, 256, 0, s>>>(t0, n_words, st->sizes[0], d_occ); ++g_launches;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(g_ctx.h_scratch + 1, d_occ, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(g_ctx.h_scratch + 2, st->d_n_unique, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -392,6 +426,7 @@ extern "C" int gt_storage_set_n_unique(gt_storage* st, uint64_t n_unique) {
 extern "C" int gt_storage_update_from(gt_storage* dst, const gt_storage* src) {
     if (ensure_ctx()) return -1;
     if (!dst || !src) return fail("gt_storage_update_from: NULL storage");
+    if (dst->world > 1 || src->world > 1) return fail("gt_storage_update_from: not available on a sharded storage");
     if (dst->kind != GT_STORAGE_BIT || src->kind != GT_STORAGE_BIT)
         return fail("gt_storage_update_from: only BitStorage can be unioned (bitstorage.cc:103-137)");
     if (dst->n != src->n || memcmp(dst->sizes, src->sizes, sizeof(uint64_t) * dst->n) != 0)
@@ -705,6 +740,7 @@ static int check_mode(const char* who, int mode) {
 }
 
 static int launch_insert(gt_storage* st, int shifter, const gt_batch& b, int K, int mode, uint64_t* d_n_new, cudaStream_t s) {
+    if (st->world > 1) return fail("a sharded storage takes GT_MODE_BLIND inserts through its exchange only (attach it first)");
     WalkArgs a = make_args(b, K);
     a.n_unique = st->d_n_unique;
     a.n_new = d_n_new;
@@ -743,34 +779,38 @@ extern "C" int64_t gt_insert_sequences(gt_storage* st, int shifter, int K, const
     if (!st) return fail("gt_insert_sequences: NULL storage");
     if (check_mode("gt_insert_sequences", mode)) return -1;
     if (n_new_per_read && mode == GT_MODE_BLIND) return fail("gt_insert_sequences: n_new_per_read needs GT_MODE_FAST or GT_MODE_EXACT");
-    if (validate_offsets("gt_insert_sequences", offsets, n_reads)) return -1;
     if (n_reads == 0) return 0;
     CU(cudaSetDevice(g_ctx.device));
     if (mode != GT_MODE_BLIND && pending_flush_sync(st)) return -1;  // is_new must see every earlier insert
+    if (offsets[n_reads] < offsets[0]) return fail("gt_insert_sequences: offsets must be non-decreasing");
     std::vector<uint64_t> cuts;
     chunk_ranges(offsets, n_reads, cuts);
-    // host-side upper bound of each chunk's k-mers (invalid reads only lower it)
-    std::vector<uint64_t> chunk_kmers(cuts.size() - 1, 0);
-    uint64_t call_kmers = 0, max_chunk = 0;
-    for (size_t c = 0; c + 1 < cuts.size(); ++c) {
-        uint64_t k = 0;
-        for (uint64_t r = cuts[c]; r < cuts[c + 1]; ++r) {
-            uint64_t len = offsets[r + 1] - offsets[r];
-            if (len >= (uint64_t)K) k += len - K + 1;
-        }
-        chunk_kmers[c] = k;
-        call_kmers += k;
-        max_chunk = std::max(max_chunk, k);
-    }
-    const bool bucketed = !n_new_per_read && bucket_usable(st, mode, K, max_chunk, call_kmers);
+    // cheap estimate of the call's k-mers (exact when every read is >= K); the per-read pass over
+    // the offsets is done chunk by chunk below so that it overlaps the GPU work of earlier chunks
+    const uint64_t call_bases = offsets[n_reads] - offsets[0];
+    const uint64_t call_est = call_bases > n_reads * (uint64_t)(K - 1) ? call_bases - n_reads * (uint64_t)(K - 1) : 0;
+    const bool bucket_call = !n_new_per_read && bucket_usable(st, mode, K, 0, call_est);
     // k-mer total accumulates on the device across chunks (scratch[3]); read once at the end
     unsigned long long* d_tot = g_ctx.d_scratch + 3;
     CU(cudaMemsetAsync(d_tot, 0, sizeof(unsigned long long), g_ctx.slot[0].stream));
     CU(cudaStreamSynchronize(g_ctx.slot[0].stream));
+    bool any_bucketed = false;
     for (size_t c = 0; c + 1 < cuts.size(); ++c) {
         Slot& sl = g_ctx.slot[c & 1];
         cudaStream_t s = sl.stream;
         uint64_t r0 = cuts[c], r1 = cuts[c + 1], nr = r1 - r0;
+        // validate this chunk's offsets and count its k-mers (invalid reads only lower the count)
+        uint64_t chunk_kmers = 0;
+        for (uint64_t r = r0; r < r1; ++r) {
+            if (offsets[r + 1] < offsets[r]) {
+                cudaDeviceSynchronize();
+                return fail("gt_insert_sequences: offsets must be non-decreasing (read %llu)", (unsigned long long)r);
+            }
+            uint64_t len = offsets[r + 1] - offsets[r];
+            chunk_kmers += len >= (uint64_t)K ? len - (uint64_t)K + 1 : 0;
+        }
+        const bool bucketed = bucket_call && chunk_kmers <= st->pend->budget_kmers;
+        any_bucketed |= bucketed;
         gt_batch view;
         if (sl.consumed_pending) {  // the compute stream may still be reading this slot's buffers
             CU(cudaStreamWaitEvent(s, sl.consumed, 0));
@@ -794,7 +834,7 @@ extern "C" int64_t gt_insert_sequences(gt_storage* st, int shifter, int K, const
             // copies + pack ran on the slot stream; hashing/bucketing runs on the compute stream
             CU(cudaEventRecord(sl.packed, s));
             CU(cudaStreamWaitEvent(g_ctx.main, sl.packed, 0));
-            if (bucket_insert(st, shifter, view, K, chunk_kmers[c])) return -1;
+            if (bucket_insert(st, shifter, view, K, chunk_kmers)) return -1;
             CU(cudaEventRecord(sl.consumed, g_ctx.main));
             sl.consumed_pending = true;
         } else if (launch_insert(st, shifter, view, K, mode, d_n_new, s)) {
@@ -805,7 +845,7 @@ extern "C" int64_t gt_insert_sequences(gt_storage* st, int shifter, int K, const
     }
     CU(cudaStreamSynchronize(g_ctx.slot[0].stream));
     CU(cudaStreamSynchronize(g_ctx.slot[1].stream));
-    if (bucketed) {
+    if (any_bucketed) {
         CU(cudaStreamSynchronize(g_ctx.main));
         g_ctx.slot[0].consumed_pending = g_ctx.slot[1].consumed_pending = false;
     }
@@ -866,6 +906,132 @@ extern "C" int64_t gt_insert_sequences_dev(gt_storage* st, int shifter, int K, c
     return (int64_t)g_ctx.h_scratch[3];
 }
 
+// ------------------------------------------------------------------------------------------
+// sharded storage: one process per GPU, table t cut into per-rank slot ranges (bucket_host.inc)
+// ------------------------------------------------------------------------------------------
+extern "C" int gt_shard_plan(int kind, const uint64_t* tablesizes, int n_tables, int world, uint64_t budget_kmers,
+                             int slice_log2_bytes, int32_t* shift_nb, int32_t* table, int32_t* owner, uint64_t* slot0,
+                             uint64_t* slots, uint32_t* cap, uint64_t* own_lo, uint64_t* own_hi) {
+    if (kind < 0 || kind > 2 || !tablesizes || n_tables < 1 || n_tables > MAX_TABLES || world < 1 || !shift_nb)
+        return fail("gt_shard_plan: bad argument");
+    for (int i = 0; i < n_tables; ++i)
+        if (tablesizes[i] == 0) return fail("gt_shard_plan: empty table");
+    PlanHost P;
+    if (make_plan(kind, tablesizes, n_tables, world, budget_kmers, slice_log2_bytes > 0 ? slice_log2_bytes : 25, P)) return -1;
+    shift_nb[0] = P.shift;
+    shift_nb[1] = P.nb;
+    for (int b = 0; b < P.nb; ++b) {
+        if (table) table[b] = P.table[b];
+        if (owner) owner[b] = P.owner[b];
+        if (slot0) slot0[b] = P.slot0[b];
+        if (slots) slots[b] = P.slots[b];
+        if (cap) cap[b] = P.cap[b];
+    }
+    for (size_t k = 0; k < P.own_lo.size(); ++k) {
+        if (own_lo) own_lo[k] = P.own_lo[k];
+        if (own_hi) own_hi[k] = P.own_hi[k];
+    }
+    return 0;
+}
+
+extern "C" gt_storage* gt_storage_create_sharded(int kind, const uint64_t* tablesizes, int n_tables, int rank, int world,
+                                                  uint64_t budget_kmers, int slice_log2_bytes) {
+    if (ensure_ctx()) return nullptr;
+    if (world < 1 || rank < 0 || rank >= world) { fail("gt_storage_create_sharded: rank %d of %d", rank, world); return nullptr; }
+    if (kind < 0 || kind > 2 || !tablesizes || n_tables < 1 || n_tables > MAX_TABLES) { fail("gt_storage_create_sharded: bad argument"); return nullptr; }
+    if (budget_kmers == 0 || budget_kmers > (1ull << 31)) { fail("gt_storage_create_sharded: budget_kmers must be 1..2^31"); return nullptr; }
+    Pending* p = new Pending();
+    if (make_plan(kind, tablesizes, n_tables, world, budget_kmers, slice_log2_bytes > 0 ? slice_log2_bytes : 25, p->host)) { delete p; return nullptr; }
+    gt_storage* st = storage_create(kind, tablesizes, n_tables, rank, world, p->host.own_lo.data() + (size_t)rank * n_tables,
+                                    p->host.own_hi.data() + (size_t)rank * n_tables);
+    if (!st) { delete p; return nullptr; }
+    p->budget_kmers = budget_kmers;
+    st->pend = p;
+    return st;
+}
+
+extern "C" int gt_storage_local_range(const gt_storage* st, int i, uint64_t* lo, uint64_t* hi) {
+    if (!st || i < 0 || i >= st->n || !lo || !hi) return fail("gt_storage_local_range: bad argument");
+    *lo = st->own_lo[i];
+    *hi = st->own_hi[i];
+    return 0;
+}
+
+extern "C" int gt_storage_attach_exchange(gt_storage* st, void* outbox, void* inbox, void* fill_send, void* fill_recv) {
+    if (ensure_ctx()) return -1;
+    if (!st || !st->pend || st->world < 2) return fail("gt_storage_attach_exchange: not a sharded storage");
+    if (!outbox || !inbox || !fill_send || !fill_recv) return fail("gt_storage_attach_exchange: NULL buffer");
+    Pending* p = st->pend;
+    if (p->attached) return fail("gt_storage_attach_exchange: already attached");
+    const PlanHost& H = p->host;
+    const int nb = H.nb, W = st->world, me = st->rank;
+    std::vector<int> owned;  // my buckets, increasing b
+    std::vector<uint64_t> R(W, 0);
+    for (int b = 0; b < nb; ++b) {
+        R[H.owner[b]] += H.cap[b];
+        if (H.owner[b] == me) owned.push_back(b);
+    }
+    const int n_owned = (int)owned.size();
+    if (pending_alloc_common(st, p, n_owned * W)) return -1;
+    // outbox: regions of the peers in rank order (skipping me), then my own region
+    std::vector<uint64_t> region_start(W, 0);
+    uint64_t off = 0;
+    for (int q = 0; q < W; ++q) if (q != me) { region_start[q] = off; off += R[q]; }
+    region_start[me] = off;
+    off += R[me];
+    std::vector<uint64_t> in_region(nb, 0);  // offset of bucket b inside its owner's region
+    {
+        std::vector<uint64_t> run(W, 0);
+        for (int b = 0; b < nb; ++b) { in_region[b] = run[H.owner[b]]; run[H.owner[b]] += H.cap[b]; }
+    }
+    uint32_t* ob = static_cast<uint32_t*>(outbox);
+    uint32_t* ib = static_cast<uint32_t*>(inbox);
+    std::vector<uint32_t*> ptrs(nb);
+    for (int b = 0; b < nb; ++b) ptrs[b] = ob + region_start[H.owner[b]] + in_region[b];
+    CU(cudaMemcpy(p->d_bptr, ptrs.data(), nb * sizeof(uint32_t*), cudaMemcpyHostToDevice));
+    // apply items: slice-major, then source rank
+    std::vector<ApplyItem> items;
+    items.reserve((size_t)n_owned * W);
+    const uint32_t* fr = static_cast<const uint32_t*>(fill_recv);
+    for (int j = 0; j < n_owned; ++j) {
+        const int b = owned[j];
+        for (int q = 0; q < W; ++q) {
+            const uint32_t* src;
+            if (q == me) src = ptrs[b];
+            else src = ib + (uint64_t)(q < me ? q : q - 1) * R[me] + in_region[b];
+            items.push_back(ApplyItem{src, fr + (size_t)q * n_owned + j, H.slot0[b], H.cap[b], (uint32_t)H.table[b]});
+        }
+    }
+    if (pending_set_items(p, items)) return -1;
+    p->d_bfill = static_cast<uint32_t*>(fill_send);
+    p->own_bfill = false;
+    p->plan.bfill = p->d_bfill;
+    CU(cudaMemset(p->d_bfill, 0, (size_t)nb * 4));
+    p->entries_total = off;
+    p->attached = true;
+    return 0;
+}
+
+// K2 over this rank's slices: its own buckets plus what the peers sent (fill_recv holds the
+// counts).  Asynchronous on the compute stream; empties this rank's cursors for the next round.
+extern "C" int gt_storage_apply(gt_storage* st) {
+    if (ensure_ctx()) return -1;
+    if (!st) return fail("gt_storage_apply: NULL storage");
+    if (!st->pend) return 0;
+    if (st->world > 1 && !st->pend->attached) return fail("gt_storage_apply: exchange buffers not attached");
+    if (st->world > 1) st->pend->pending_kmers = std::max<uint64_t>(st->pend->pending_kmers, 1);  // peers may have sent even if we did not
+    return pending_flush_async(st);
+}
+
+// Run this library's kernels on a stream of the caller (e.g. torch's current stream) so that
+// they order with the caller's collectives; NULL restores the library's own stream.
+extern "C" int gt_set_compute_stream(void* stream) {
+    if (ensure_ctx()) return -1;
+    CU(cudaDeviceSynchronize());
+    g_ctx.main = stream ? static_cast<cudaStream_t>(stream) : g_ctx.own_main;
+    return 0;
+}
+
 // Apply every pending (write-combined) insert of `st` to its tables and wait for it.
 extern "C" int gt_storage_flush(gt_storage* st) {
     if (ensure_ctx()) return -1;
@@ -880,16 +1046,18 @@ extern "C" int gt_storage_pending_info(gt_storage* st, uint64_t* info) {
     memset(info, 0, 8 * sizeof(uint64_t));
     if (!st->pend) return 0;
     Pending* p = st->pend;
-    unsigned long long nd = 0;
+    unsigned long long nd[2] = {0, 0};
     CU(cudaDeviceSynchronize());
-    CU(cudaMemcpy(&nd, p->d_n_direct, 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(nd, p->d_counters, 16, cudaMemcpyDeviceToHost));
+    if (nd[1]) return fail("sharded insert dropped %llu updates that overflowed a bucket of a slice held by another rank "
+                           "(skewed input: lower the k-mers per round)", nd[1]);
     info[0] = 1;
-    info[1] = (uint64_t)p->n_buckets;
+    info[1] = (uint64_t)p->host.nb;
     info[2] = (uint64_t)p->plan.shift;
     info[3] = p->budget_kmers;
     info[4] = p->entries_total;
     info[5] = p->pending_kmers;
-    info[6] = nd;
+    info[6] = nd[0];
     info[7] = p->total_chunks;
     return 0;
 }
@@ -1002,6 +1170,7 @@ extern "C" int64_t gt_query_sequences(gt_storage* st, int shifter, int K, const 
                                        uint64_t n_reads, int16_t* counts, uint8_t* status) {
     if (check_reads("gt_query_sequences", bases, offsets, n_reads, K)) return -1;
     if (!st || !counts) return fail("gt_query_sequences: NULL argument");
+    if (st->world > 1) return fail("gt_query_sequences: not available on a sharded storage (query the owner ranks)");
     if (pending_flush_sync(st)) return -1;
     if (validate_offsets("gt_query_sequences", offsets, n_reads)) return -1;
     if (n_reads == 0) return 0;
@@ -1023,6 +1192,7 @@ extern "C" int64_t gt_median_count_at_least(gt_storage* st, int shifter, int K, 
                                              uint64_t n_reads, uint32_t cutoff, uint8_t* pass, uint8_t* status) {
     if (check_reads("gt_median_count_at_least", bases, offsets, n_reads, K)) return -1;
     if (!st || !pass) return fail("gt_median_count_at_least: NULL argument");
+    if (st->world > 1) return fail("gt_median_count_at_least: not available on a sharded storage");
     if (pending_flush_sync(st)) return -1;
     if (validate_offsets("gt_median_count_at_least", offsets, n_reads)) return -1;
     if (n_reads == 0) return 0;
@@ -1072,6 +1242,7 @@ static void launch_insert_hashes_t(const gt_storage* st, const uint64_t* d_h, ui
 extern "C" int gt_insert_hashes(gt_storage* st, const uint64_t* hashes, uint64_t n, int mode, uint8_t* is_new) {
     if (ensure_ctx()) return -1;
     if (!st || (n && !hashes)) return fail("gt_insert_hashes: NULL argument");
+    if (st->world > 1) return fail("gt_insert_hashes: not available on a sharded storage");
     if (check_mode("gt_insert_hashes", mode)) return -1;
     if (is_new && mode == GT_MODE_BLIND) return fail("gt_insert_hashes: is_new needs GT_MODE_FAST or GT_MODE_EXACT");
     if (mode != GT_MODE_BLIND && pending_flush_sync(st)) return -1;  // is_new must see every earlier insert
@@ -1106,6 +1277,7 @@ extern "C" int gt_insert_hashes(gt_storage* st, const uint64_t* hashes, uint64_t
 extern "C" int gt_query_hashes(gt_storage* st, const uint64_t* hashes, uint64_t n, int16_t* counts) {
     if (ensure_ctx()) return -1;
     if (!st || (n && (!hashes || !counts))) return fail("gt_query_hashes: NULL argument");
+    if (st->world > 1) return fail("gt_query_hashes: not available on a sharded storage");
     if (pending_flush_sync(st)) return -1;
     if (n == 0) return 0;
     CU(cudaSetDevice(g_ctx.device));

@@ -167,6 +167,9 @@ int64_t gt_insert_sequences_dev(gt_storage* st, int shifter, int K, const void* 
  * update_from, tracked inserts) applies what is pending first, so the semantics of
  * Storage::insert (bitstorage.hh:195-219 etc.) are unchanged; gt_storage_flush forces it. */
 int gt_storage_flush(gt_storage* st);
+/* Queue the apply of what is pending on the compute stream without waiting (gt_storage_flush
+ * = this + wait).  On a sharded storage this is the step after the bucket exchange. */
+int gt_storage_apply(gt_storage* st);
 /* diagnostics: info[8] = {store built, n_buckets, log2(slots per slice), k-mer budget between
  * flushes, entries allocated, pending k-mers (upper bound), updates that overflowed a bucket
  * and were applied directly, apply-grid size} */
@@ -182,6 +185,39 @@ double gt_timer_elapsed_ms(int from_slot, int to_slot);
  * ms3/n3 = {k_bucket, k_apply, k_walk} accumulated since gt_profile_enable(1). */
 int gt_profile_enable(int on);
 int gt_profile_get(double* ms3, uint64_t* n3);
+
+/* ---- sharded storage: one process per GPU (no counterpart in the reference) -------------- */
+/* Table t is cut into slices of 2^shift slots; rank r of `world` holds a contiguous run of
+ * slices of every table, so concatenating the ranks' parts in rank order gives exactly the
+ * single-GPU / reference table.  Every rank hashes its own reads, buckets the updates by slice
+ * (k_bucket), ships the buckets of foreign slices to their owners, and applies what it
+ * receives (k_apply).  The exchange itself belongs to the caller (goetia_b200/shard.py does it
+ * with NCCL all-to-all); these entry points define the plan and the buffer layout.
+ *
+ * gt_shard_plan: host arithmetic only (no GPU needed).  shift_nb[2] = {log2(slots per slice),
+ * number of buckets}; per bucket: table, owner rank, first slot, slots, capacity in entries
+ * per producer and round (arrays of >= 1024 elements); own_lo/own_hi[world * n_tables] = slot
+ * range of table t on rank r at [r * n_tables + t].  slice_log2_bytes <= 0 selects 32 MB. */
+int gt_shard_plan(int kind, const uint64_t* tablesizes, int n_tables, int world, uint64_t budget_kmers,
+                  int slice_log2_bytes, int32_t* shift_nb, int32_t* table, int32_t* owner, uint64_t* slot0,
+                  uint64_t* slots, uint32_t* cap, uint64_t* own_lo, uint64_t* own_hi);
+/* This rank's part of a storage sharded over `world` ranks.  budget_kmers = the most k-mers
+ * one rank buckets between two exchanges.  gt_storage_download_table returns the local part
+ * (gt_storage_table_bytes bytes, laid out as that part of the reference's table). */
+gt_storage* gt_storage_create_sharded(int kind, const uint64_t* tablesizes, int n_tables, int rank, int world,
+                                      uint64_t budget_kmers, int slice_log2_bytes);
+int gt_storage_local_range(const gt_storage* st, int i, uint64_t* lo, uint64_t* hi);
+/* Device buffers of the exchange (caller-owned, e.g. torch tensors), all uint32:
+ *   outbox    [sum of all regions]  regions of the peers in rank order (skipping this rank),
+ *                                   then this rank's own region; a region = the buckets its
+ *                                   owner holds, in bucket order, `cap` entries each
+ *   inbox     [(world-1) * R_me]    one copy of this rank's region per peer, in rank order
+ *   fill_send [n_buckets]           entry count of every bucket produced here (bucket order)
+ *   fill_recv [world * n_owned]     [q][j] = count rank q produced for this rank's j-th bucket */
+int gt_storage_attach_exchange(gt_storage* st, void* outbox, void* inbox, void* fill_send, void* fill_recv);
+/* Run the library's kernels on a caller-owned CUDA stream (NULL = the library's own), so that
+ * they order with the caller's collectives on that stream. */
+int gt_set_compute_stream(void* stream);
 
 /* ---- SourmashSketch (sketches/sourmash_sketch.hh:24-82) -------------------------------- */
 /* Sketch(n, K, is_protein=false, dayhoff=false, hp=false, seed, scaled):

@@ -1,0 +1,149 @@
+"""Worker of the multi-rank tests (one process per rank; RANK / WORLD_SIZE / MASTER_* from the env).
+
+    python tests/shard_worker.py cpu  KIND   -- gloo; the two kernels are emulated with numpy on top of the oracle's
+                                                hashes, so what is tested is the plan, the buffer layout and the
+                                                all-to-all bookkeeping of goetia_b200/shard.py (no GPU needed)
+    python tests/shard_worker.py cuda KIND   -- nccl; the real library on one GPU per rank
+
+Rank 0 gathers every rank's table parts, concatenates them in rank order and compares them byte
+for byte with the oracle's tables after the same reads.  Exit code 0 = equal.
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from goetia_b200.shard import ShardExchange, ShardPlan  # noqa: E402
+from oracle.binding import Port  # noqa: E402
+from tests.util import genome_reads  # noqa: E402
+
+
+def part_bytes(kind, lo, hi, last):
+    if hi <= lo:
+        return 0
+    if kind == 0:
+        return hi // 8 + 1 - lo // 8 if last else (hi - lo) // 8
+    if kind == 1:
+        return hi - lo
+    return hi // 2 + 1 - lo // 2 if last else (hi - lo) // 2
+
+
+def np_apply(kind, slab, local_slots):
+    """Emulates k_apply on a local part (slot indices relative to the part's first slot)."""
+    if kind == 0:
+        np.bitwise_or.at(slab, local_slots >> 3, (1 << (local_slots & 7)).astype(np.uint8))
+    elif kind == 1:
+        cnt = np.bincount(local_slots, minlength=slab.size)[:slab.size]
+        slab[:] = np.minimum(255, slab.astype(np.int64) + cnt).astype(np.uint8)
+    else:
+        cnt = np.bincount(local_slots, minlength=2 * slab.size)
+        for par, sh in ((1, 0), (0, 4)):  # odd slot = low nibble, even slot = high nibble
+            c = cnt[par::2][:slab.size]
+            cur = (slab >> sh) & 15
+            new = np.minimum(15, cur.astype(np.int64) + c[:slab.size]).astype(np.uint8)
+            slab[:] = (slab & (0xF0 if sh == 0 else 0x0F)) | (new << sh)
+
+
+def main():
+    mode, kind = sys.argv[1], int(sys.argv[2])
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    K = [31, 21, 25][kind]
+    x_size = int(os.environ.get("SHARD_TABLE_X", "300000"))
+    n_reads = int(os.environ.get("SHARD_READS", "600"))
+    sizes = Port.primes_near(4, x_size)
+    bases, offsets = genome_reads(n_reads, 100, 4000, seed=5 + kind)
+    per = (n_reads + world - 1) // world
+    r0, r1 = min(n_reads, rank * per), min(n_reads, (rank + 1) * per)
+    my_b = bases[int(offsets[r0]):int(offsets[r1])]
+    my_o = offsets[r0:r1 + 1] - offsets[r0]
+    budget = max(1024, per * 100)  # gt_insert_sequences_dev bounds a batch by its bases
+    slice_log2 = int(os.environ.get("SHARD_SLICE_LOG2", "10"))
+
+    if mode == "cpu":
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        plan = ShardPlan(kind, sizes, world, budget, slice_log2)
+        x = ShardExchange(plan, rank, torch, "cpu")
+        first = [int(np.nonzero(plan.table == t)[0][0]) for t in range(len(sizes))]
+        fill = np.zeros(plan.nb, dtype=np.int64)
+        outbox = x.outbox.numpy()
+        for r in range(my_o.size - 1):
+            seq = my_b[int(my_o[r]):int(my_o[r + 1])].tobytes()
+            fw, rc = Port.hash_sequence(1, K, seq)
+            h = np.minimum(fw, rc)
+            for t, size in enumerate(sizes):
+                bins = h % np.uint64(size)
+                bs = first[t] + (bins >> np.uint64(plan.shift)).astype(np.int64)
+                offs = (bins & np.uint64((1 << plan.shift) - 1)).astype(np.int64)
+                for b, o in zip(bs, offs):
+                    assert fill[b] < plan.cap[b]
+                    outbox[x.bucket_off[b] + fill[b]] = o
+                    fill[b] += 1
+        x.fill_send[:plan.nb] = torch.from_numpy(fill.astype(np.int32))
+        x.exchange()
+        parts = []
+        for t, size in enumerate(sizes):
+            lo, hi = int(plan.own_lo[rank, t]), int(plan.own_hi[rank, t])
+            slab = np.zeros(part_bytes(kind, lo, hi, hi == size), dtype=np.uint8)
+            for j, b in enumerate(plan.owned[rank]):
+                if plan.table[b] != t:
+                    continue
+                for q in range(world):
+                    ent = x.source_view(q, j).numpy().astype(np.int64)
+                    if ent.size:
+                        np_apply(kind, slab, int(plan.slot0[b]) - lo + ent)
+            parts.append(slab)
+    else:
+        import goetia_b200 as gb
+        from goetia_b200 import _capi
+        from goetia_b200.shard import ShardedStorage
+        local = int(os.environ.get("LOCAL_RANK", rank))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        gb.init(local)
+        st = ShardedStorage(kind, sizes, budget, slice_log2_bytes=slice_log2)
+        plan = st.plan
+        d_b = torch.from_numpy(my_b.copy()).cuda()
+        d_o = torch.from_numpy(my_o.astype(np.int64)).cuda()
+        torch.cuda.synchronize()
+        rounds = int(os.environ.get("SHARD_ROUNDS", "2"))
+        for _ in range(rounds):  # the same reads twice: counters must count both passes
+            nk = st.bucket_sequences_dev(_capi.SHIFTER_CAN, K, d_b.data_ptr(), d_o.data_ptr(), my_o.size - 1, my_b.size)
+            assert nk == (my_o.size - 1) * (100 - K + 1), nk
+            st.exchange_and_apply()
+        st.synchronize()
+        info = st.pending_info()
+        assert info["pending_kmers"] == 0
+        parts = st.local_tables()
+
+    # gather the parts on rank 0 and compare with the oracle
+    ok = True
+    gathered = [None] * world
+    dist.gather_object([p.tobytes() for p in parts], gathered if rank == 0 else None, dst=0)
+    if rank == 0:
+        ref = Port(kind, 1, K, sizes)
+        passes = 1 if mode == "cpu" else int(os.environ.get("SHARD_ROUNDS", "2"))
+        for _ in range(passes):
+            ref.insert_reads(bases, offsets)
+        for t, want in enumerate(ref.tables()):
+            got = np.frombuffer(b"".join(gathered[r][t] for r in range(world)), dtype=np.uint8)
+            if got.size != want.size or not np.array_equal(got, want):
+                ok = False
+                print("table %d differs (%d vs %d bytes, %d mismatches)" % (
+                    t, got.size, want.size, int((got[:min(got.size, want.size)] != want[:min(got.size, want.size)]).sum())))
+        print("shard_worker %s kind=%d world=%d shift=%d buckets=%d: %s" % (mode, kind, world, plan.shift, plan.nb,
+                                                                          "tables bit-exact" if ok else "MISMATCH"))
+    flag = torch.tensor([1 if ok else 0])
+    if mode == "cuda":
+        flag = flag.cuda()
+    dist.broadcast(flag, src=0)
+    dist.destroy_process_group()
+    return 0 if int(flag.item()) else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
