@@ -15,9 +15,9 @@
 // DRAM bytes per k-mer (4 tables): 16 B bucket write + 16 B bucket read + the table streamed
 // once per flush, against 256 B algorithmic (4 x (32 B sector read + 32 B write-back)).
 //
-//   K1b k_bucket      : stage packed tile -> roll both cyclic hashes -> n_tables fastmods ->
-//                       CTA-local counting sort by slice in shared memory -> one global
-//                       cursor reservation per (tile, slice) -> coalesced run copies.
+//   K1b k_bucket      : stage packed tile -> roll both cyclic hashes -> n_tables reductions ->
+//                       append to per-slice staging rows in shared memory -> one global
+//                       cursor reservation per (sub-step, slice) -> 16 B run copies.
 //   K2  k_apply       : CTA = one 4096-entry chunk of one bucket, buckets in blockIdx (= slice) order;
 //                       16 B streaming loads of entries, RED.OR / CAS into the slice.
 #pragma once
@@ -44,8 +44,15 @@ struct ProducePlan {
     uint32_t first[MAX_TABLES + 1];   // first bucket id of table t
     uint64_t own_lo[MAX_TABLES];      // slots [own_lo, own_hi) of table t are held by this rank
     uint64_t own_hi[MAX_TABLES];
+    // cheap exact h % size for tables of >= 2^28 slots (see bin_of): dsh = size << rs >= 2^32,
+    // m32 = floor((2^64-1) / dsh) < 2^32; rs < 0 selects the generic 64-bit fastmod
+    uint64_t dsh[MAX_TABLES];
+    uint32_t m32[MAX_TABLES];
+    int32_t rs[MAX_TABLES];
+    uint32_t stage_cap;               // shared-memory staging entries per bucket and sub-step (multiple of 4)
+    uint32_t piece;                   // entries a CTA takes from a bucket's cursor at a time (0: exact-size requests)
     uint32_t* const* bptr;            // [n_buckets] entry array of each bucket
-    const uint32_t* bcap;             // [n_buckets] capacity in entries
+    const uint32_t* bcap;             // [n_buckets] capacity in entries (multiple of 4)
     uint32_t* bfill;                  // [n_buckets] cursor; can exceed bcap (excess handled at once)
     unsigned long long* n_direct;     // updates that overflowed a bucket and were applied directly
     unsigned long long* n_dropped;    // overflowed updates of slots this rank does not hold (an error)
@@ -60,11 +67,59 @@ struct ApplyItem {
     uint32_t table;
 };
 
+constexpr uint32_t BK_PAD = 0xFFFFFFFFu;  // filler entry (runs are padded to 16 B); never a valid offset (shift <= 31)
+
+// h % d, bit-exact, for d with dsh = d << rs in [2^32, 2^63]: the reciprocal m32 = floor((2^64-1)/dsh)
+// then fits 32 bits, so mulhi64(h, m32) is two 32x32 products; it is floor(h/dsh) or one less
+// (same argument as fastmod_u64), one conditional subtract gives h % dsh, and h % d follows by
+// rs (<= 4) more conditional subtracts of d << j.
+__device__ __forceinline__ uint64_t bin_of(uint64_t h, uint64_t d, uint64_t magic, uint64_t dsh, uint32_t m32, int rs) {
+    if (rs < 0) return fastmod_u64(h, d, magic);
+    const uint32_t hl = (uint32_t)h, hh = (uint32_t)(h >> 32);
+    const uint64_t u = (uint64_t)hh * m32 + __umulhi(hl, m32);  // < 2^64
+    const uint32_t q = (uint32_t)(u >> 32);
+    const uint64_t qd = (uint64_t)q * (uint32_t)dsh + ((uint64_t)(q * (uint32_t)(dsh >> 32)) << 32);
+    uint64_t r = h - qd;
+    if (r >= dsh) r -= dsh;
+    for (int j = rs - 1; j >= 0; --j) {  // rs is uniform (per table); 0 iterations for tables of >= 2^32 slots
+        const uint64_t dj = d << j;
+        if (r >= dj) r -= dj;
+    }
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------
-// K1b
+// K1b.  One CTA = 8192 consecutive k-mer start positions of the flat packed stream (as k_walk),
+// processed in 4 sub-steps of 8 positions per thread.  Every update is appended to its
+// bucket's staging row in shared memory (one returning shared atomic per update); after each
+// sub-step the rows are copied out: one global cursor reservation per (sub-step, bucket),
+// runs padded to 16 B and written with 16 B stores.  A row that is full (skewed input) spills
+// the update straight to the bucket / the table, so nothing is ever lost.
 // ------------------------------------------------------------------------------------------
+constexpr int BK_SUB = 8;  // positions per thread and sub-step
+constexpr int BK_OWN = BK_MAX_BUCKETS / TILE_THREADS;  // buckets a lane may own (4)
+constexpr uint32_t BK_NONE = 0xFFFFFFFFu;
+
+template <int KIND>
+__device__ __forceinline__ void bucket_spill(const TableSet& ts, const ProducePlan& bp, int t, uint32_t b, uint32_t off,
+                                             unsigned long long& direct, unsigned long long& dropped) {
+    // slow path: a 16 B group holding this one entry, or -- bucket full -- the table itself
+    const uint32_t g = atomicAdd(bp.bfill + b, 4u), cap = __ldg(bp.bcap + b);
+    if (g < cap) {
+        *reinterpret_cast<uint4*>(bp.bptr[b] + g) = make_uint4(off, BK_PAD, BK_PAD, BK_PAD);
+        return;
+    }
+    const uint64_t bin = ((uint64_t)(b - bp.first[t]) << bp.shift) + off;
+    if (bin >= bp.own_lo[t] && bin < bp.own_hi[t]) {
+        slot_insert<KIND, false>(ts.ptr[t], bin);
+        ++direct;
+    } else {
+        ++dropped;
+    }
+}
+
 template <int KIND, bool CAN, int NT>
-__global__ void __launch_bounds__(TILE_THREADS, 2)
+__global__ void __launch_bounds__(TILE_THREADS, 3)
 k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts, const __grid_constant__ ProducePlan bp) {
     extern __shared__ __align__(16) uint64_t smem[];
     const int K = a.K;
@@ -72,24 +127,34 @@ k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts
     const int tile_words = TILE_THREADS + halo_words;
     const int nb = bp.n_buckets;
     const int nt = NT > 0 ? NT : bp.n_tables;
-    ulonglong2* tab = reinterpret_cast<ulonglong2*>(smem);           // 8 x 16 B
-    uint64_t* hs = smem + 16;                                        // TILE_POS hashes, [i][tid]
-    uint64_t* sw = hs + TILE_POS;                                    // packed tile + halo
-    uint32_t* sorted = reinterpret_cast<uint32_t*>(sw + tile_words + (tile_words & 1));  // TILE_POS offsets
-    uint32_t* hist = sorted + TILE_POS;                              // [nb] updates of this tile per bucket
-    uint32_t* cur = hist + nb;                                       // [nb] scatter cursor (run end after scatter)
-    uint32_t* gpos = cur + nb;                                       // [nb] reserved position in the global bucket
+    const uint32_t C = bp.stage_cap;                                 // staging entries per bucket (multiple of 4)
+    ulonglong2* tab = reinterpret_cast<ulonglong2*>(smem);           // 8 x 16 B: per-base roll constants
+    ulonglong2* tab2 = tab + 8;                                      // 16 x 16 B: per-base-pair seed constants {fw, rc}
+    uint64_t* sw = smem + 48;                                        // packed tile + halo
+    uint32_t* stage = reinterpret_cast<uint32_t*>(sw + tile_words + (tile_words & 1));  // [nb][C]
+    uint32_t* cnt = stage + (size_t)nb * C;                          // [2][nb] appends of this / the next sub-step
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 4) {
         tab[tid] = make_ulonglong2(lemire_T(tid), rotl64(lemire_T(3 - tid), (unsigned)K));
         tab[4 + tid] = make_ulonglong2(rotl64(lemire_T(tid), (unsigned)K), lemire_T(3 - tid));
     }
+    if (tid < 16) {
+        // two bases c0 (first), c1: forward eats c0 then c1; the reverse strand sees comp(c1) first
+        const int c0 = tid & 3, c1 = tid >> 2;
+        tab2[tid] = make_ulonglong2(rotl1(lemire_T(c0)) ^ lemire_T(c1), lemire_T(3 - c0) ^ rotl1(lemire_T(3 - c1)));
+    }
+    for (int b = tid; b < 2 * nb; b += TILE_THREADS) cnt[b] = 0;
     const uint64_t n_tiles = (a.n_bases + TILE_POS - 1) / TILE_POS;
-    const uint64_t slot_mask = (1ull << bp.shift) - 1;
+    const uint32_t slot_mask = (uint32_t)((1ull << bp.shift) - 1);
     unsigned long long direct = 0, dropped = 0;
+    int phase = 0;  // which half of cnt[] the current sub-step appends to
+    const uint32_t R = bp.piece, C4 = (C + 3u) & ~3u;
+    uint32_t c_pos[BK_OWN], c_left[BK_OWN], c_nxt[BK_OWN];  // this lane's buckets: write position, room, next piece
+#pragma unroll
+    for (int rr = 0; rr < BK_OWN; ++rr) { c_pos[rr] = 0; c_left[rr] = 0; c_nxt[rr] = BK_NONE; }
 
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        __syncthreads();  // previous tile fully flushed; tab visible
+        __syncthreads();  // previous tile's words consumed; tab / cnt visible
         const uint64_t w0 = tile * TILE_THREADS;
         for (int i = tid * 2; i < tile_words; i += TILE_THREADS * 2) {
             uint64_t gi = w0 + i;
@@ -102,131 +167,181 @@ k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts
                 if (i + 1 < tile_words) sw[i + 1] = 0;
             }
         }
-        for (int b = tid; b < nb; b += TILE_THREADS) hist[b] = 0;
         __syncthreads();
 
-        // ---- phase 1: roll, count per bucket, park the hash values ---------------------------
-        uint32_t vm = 0;  // bit i: window p0+i is a k-mer of a usable read
         const uint64_t p0 = tile * TILE_POS + (uint64_t)tid * POS_PER_THREAD;
-        if (p0 < a.n_bases) {
-            uint64_t fw = 0, rc = 0;
-            for (int j = 0; j < K; ++j) {
-                int cf = (int)((sw[tid + (j >> 5)] >> (2 * (j & 31))) & 3);
-                fw = rotl1(fw) ^ tab[cf].x;
+        const bool live = p0 < a.n_bases;
+        uint64_t fw = 0, rc = 0, wo = 0, win = 0, r = 0, rend = 0;
+        bool rok = false;
+        if (live) {
+            // seed both hashes from the window at p0 (word-aligned), two bases per step:
+            //   fw = sum_j rotl(T[c_j], K-1-j)  (K "eat" steps, cyclichash.h:105-108)
+            //   rc = sum_j rotl(T[comp c_j], j) (rollinghashshifter.hh:183-197)
+            const int pairs = K >> 1;
+            if (K & 1) {
+                const int j = K - 1;
+                const int c = (int)((sw[tid + (j >> 5)] >> (2 * (j & 31))) & 3);
+                if (CAN) rc = tab[4 + c].y;  // T[comp c]; the loop below rotates it by K-1
+            }
+            for (int g = 0; g < pairs; ++g) {
+                const int nf = (int)((sw[tid + (g >> 4)] >> (4 * (g & 15))) & 15);
+                fw = rotl64(fw, 2) ^ tab2[nf].x;
                 if (CAN) {
-                    int jr = K - 1 - j;
-                    int cr = (int)((sw[tid + (jr >> 5)] >> (2 * (jr & 31))) & 3);
-                    rc = rotl1(rc) ^ tab[4 + cr].y;
+                    const int gr = pairs - 1 - g;
+                    const int nr = (int)((sw[tid + (gr >> 4)] >> (4 * (gr & 15))) & 15);
+                    rc = rotl64(rc, 2) ^ tab2[nr].y;
                 }
             }
-            const uint64_t wo = sw[tid];
-            uint64_t win;
+            if (K & 1) {
+                const int j = K - 1;
+                const int c = (int)((sw[tid + (j >> 5)] >> (2 * (j & 31))) & 3);
+                fw = rotl1(fw) ^ tab[c].x;
+            }
+            wo = sw[tid];
             {
                 int a0 = tid + ((K - 1) >> 5);
                 unsigned sh = 2u * (unsigned)((K - 1) & 31);
                 win = sh ? (sw[a0] >> sh) | (sw[a0 + 1] << (64u - sh)) : sw[a0];
             }
-            uint64_t r = __ldg(a.coarse + (p0 >> COARSE_SHIFT));
-            uint64_t rend = __ldg(a.offsets + r + 1) - a.base0;
-            {
-                int steps = 0;
-                while (rend <= p0) {
-                    if (++steps > 8) {
-                        r = find_read(a.offsets, a.n_reads, p0 + a.base0);
-                        rend = __ldg(a.offsets + r + 1) - a.base0;
-                        break;
-                    }
-                    ++r;
+            r = __ldg(a.coarse + (p0 >> COARSE_SHIFT));
+            rend = __ldg(a.offsets + r + 1) - a.base0;
+            int steps = 0;
+            while (rend <= p0) {
+                if (++steps > 8) {
+                    r = find_read(a.offsets, a.n_reads, p0 + a.base0);
                     rend = __ldg(a.offsets + r + 1) - a.base0;
+                    break;
                 }
+                ++r;
+                rend = __ldg(a.offsets + r + 1) - a.base0;
             }
-            bool rok = !(__ldg(a.flags + r) & READ_INVALID);
+            rok = !(__ldg(a.flags + r) & READ_INVALID);
+        }
+
+        for (int sub = 0; sub < POS_PER_THREAD / BK_SUB; ++sub) {
+            uint32_t* cn = cnt + phase * nb;
+            // ---- append: roll, reduce, stage ------------------------------------------------------
+            if (live) {
 #pragma unroll 4
-            for (int i = 0; i < POS_PER_THREAD; ++i) {
-                const uint64_t p = p0 + i;
-                if (p >= a.n_bases) break;
-                if (i) {
-                    int out = (int)((wo >> (2 * (i - 1))) & 3);
-                    int in = (int)((win >> (2 * i)) & 3);
-                    ulonglong2 ti = tab[in], to = tab[4 + out];
-                    fw = rotl1(fw) ^ to.x ^ ti.x;
-                    if (CAN) rc = rotr1(rc ^ ti.y ^ to.y);
-                }
-                if (p >= rend) {
-                    do {
-                        ++r;
-                        rend = __ldg(a.offsets + r + 1) - a.base0;
-                    } while (p >= rend);
-                    rok = !(__ldg(a.flags + r) & READ_INVALID);
-                }
-                if (rok && p + (uint64_t)K <= rend) {
-                    const uint64_t h = CAN ? (fw < rc ? fw : rc) : fw;
-                    hs[i * TILE_THREADS + tid] = h;
-                    vm |= 1u << i;
-#pragma unroll
-                    for (int t = 0; t < nt; ++t) {
-                        uint64_t bin = fastmod_u64(h, ts.size[t], ts.magic[t]);
-                        atomicAdd(&hist[bp.first[t] + (uint32_t)(bin >> bp.shift)], 1u);
+                for (int ii = 0; ii < BK_SUB; ++ii) {
+                    const int i = sub * BK_SUB + ii;
+                    const uint64_t p = p0 + i;
+                    if (p >= a.n_bases) break;
+                    if (i) {
+                        int out = (int)((wo >> (2 * (i - 1))) & 3);
+                        int in = (int)((win >> (2 * i)) & 3);
+                        ulonglong2 ti = tab[in], to = tab[4 + out];
+                        fw = rotl1(fw) ^ to.x ^ ti.x;
+                        if (CAN) rc = rotr1(rc ^ ti.y ^ to.y);
                     }
-                }
-            }
-        }
-        __syncthreads();
-
-        // ---- reserve room in the global buckets; per-table exclusive scan of the counts -------
-        for (int b = tid; b < nb; b += TILE_THREADS) {
-            uint32_t c = hist[b];
-            gpos[b] = c ? atomicAdd(bp.bfill + b, c) : 0u;
-        }
-        for (int t = warp; t < nt; t += TILE_THREADS / 32) {
-            const int b0 = (int)bp.first[t], b1 = (int)bp.first[t + 1];
-            uint32_t run = 0;
-            for (int b = b0; b < b1; b += 32) {
-                uint32_t c = (b + lane < b1) ? hist[b + lane] : 0u, incl = c;
-                for (int o = 1; o < 32; o <<= 1) {
-                    uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                if (b + lane < b1) cur[b + lane] = run + incl - c;
-                run += __shfl_sync(0xffffffffu, incl, 31);
-            }
-        }
-        __syncthreads();
-
-        // ---- per table: scatter offsets into bucket order, then copy the runs out ---------------
-        for (int t = 0; t < nt; ++t) {
-            const uint64_t size = ts.size[t], magic = ts.magic[t];
-            const uint32_t fb = bp.first[t];
-            uint32_t m = vm;
-            while (m) {
-                int i = __ffs(m) - 1;
-                m &= m - 1;
-                uint64_t bin = fastmod_u64(hs[i * TILE_THREADS + tid], size, magic);
-                uint32_t pos = atomicAdd(&cur[fb + (uint32_t)(bin >> bp.shift)], 1u);
-                sorted[pos] = (uint32_t)(bin & slot_mask);
-            }
-            __syncthreads();
-            for (uint32_t b = fb + warp; b < bp.first[t + 1]; b += TILE_THREADS / 32) {
-                const uint32_t n = hist[b];
-                if (!n) continue;
-                const uint32_t src = cur[b] - n, g = gpos[b], cap = __ldg(bp.bcap + b);
-                uint32_t* dst = bp.bptr[b];
-                for (uint32_t e = lane; e < n; e += 32) {
-                    uint32_t off = sorted[src + e];
-                    if (g + e < cap) {
-                        dst[g + e] = off;
-                    } else {  // bucket full (skewed input): apply here, correctness never depends on capacity
-                        const uint64_t bin = ((uint64_t)(b - fb) << bp.shift) + off;
-                        if (bin >= bp.own_lo[t] && bin < bp.own_hi[t]) {
-                            slot_insert<KIND, false>(ts.ptr[t], bin);
-                            ++direct;
-                        } else {
-                            ++dropped;
+                    if (p >= rend) {
+                        do {
+                            ++r;
+                            rend = __ldg(a.offsets + r + 1) - a.base0;
+                        } while (p >= rend);
+                        rok = !(__ldg(a.flags + r) & READ_INVALID);
+                    }
+                    if (rok && p + (uint64_t)K <= rend) {
+                        const uint64_t h = CAN ? (fw < rc ? fw : rc) : fw;  // Canonical::value(), canonical.hh:124-126
+#pragma unroll
+                        for (int t = 0; t < nt; ++t) {
+                            const uint64_t bin = bin_of(h, ts.size[t], ts.magic[t], bp.dsh[t], bp.m32[t], bp.rs[t]);
+                            const uint32_t b = bp.first[t] + (uint32_t)(bin >> bp.shift);
+                            const uint32_t off = (uint32_t)bin & slot_mask;
+                            const uint32_t pos = atomicAdd(&cn[b], 1u);
+                            if (pos < C) stage[b * C + pos] = off;
+                            else bucket_spill<KIND>(ts, bp, t, b, off, direct, dropped);
                         }
                     }
                 }
             }
             __syncthreads();
+            // ---- copy the rows out.  Lane l of warp w owns buckets w + 8*l + 256*rr (rr < 4) and keeps
+            // their write position in registers: room in the global bucket is taken R entries at a
+            // time and the next piece is requested one flush ahead, so the latency of the global
+            // cursor atomic is hidden behind the next append phase (R == 0: exact-size requests).
+            uint32_t* cz = cnt + (phase ^ 1) * nb;
+#pragma unroll
+            for (int rr = 0; rr < BK_OWN; ++rr) {
+                const int base = warp + rr * TILE_THREADS;
+                if (base >= nb) break;
+                const int mine = base + 8 * lane;  // TILE_THREADS / 32 == 8 warps
+                uint32_t n = 0, d0 = 0, l0 = 0, d1 = 0, l1 = 0;
+                if (mine < nb) {
+                    n = min(cn[mine], C);
+                    cz[mine] = 0;  // the other half is idle now: clear it for the next sub-step
+                    const uint32_t n4 = (n + 3u) & ~3u;
+                    if (R == 0) {
+                        if (n4) { d0 = atomicAdd(bp.bfill + mine, n4); l0 = n4; }
+                    } else if (n4) {
+                        l0 = min(c_left[rr], n4);
+                        d0 = c_pos[rr];
+                        c_pos[rr] += l0;
+                        c_left[rr] -= l0;
+                        l1 = n4 - l0;
+                        if (l1) {  // continue in the next piece (R >= the longest run)
+                            if (c_nxt[rr] == BK_NONE) c_nxt[rr] = atomicAdd(bp.bfill + mine, R);
+                            d1 = c_nxt[rr];
+                            c_nxt[rr] = BK_NONE;
+                            c_pos[rr] = d1 + l1;
+                            c_left[rr] = R - l1;
+                        }
+                        if (c_left[rr] < C4 && c_nxt[rr] == BK_NONE) c_nxt[rr] = atomicAdd(bp.bfill + mine, R);
+                    }
+                }
+                const unsigned have = __ballot_sync(0xffffffffu, n != 0);
+                for (unsigned m = have; m; m &= m - 1) {
+                    const int l = __ffs(m) - 1;
+                    const uint32_t bn = __shfl_sync(0xffffffffu, n, l);
+                    const uint32_t bd0 = __shfl_sync(0xffffffffu, d0, l), bl0 = __shfl_sync(0xffffffffu, l0, l);
+                    const uint32_t bd1 = __shfl_sync(0xffffffffu, d1, l);
+                    const uint32_t b = (uint32_t)(base + 8 * l);
+                    const uint32_t cap = __ldg(bp.bcap + b);
+                    uint32_t* dst = bp.bptr[b];
+                    const uint32_t* row = stage + b * C;
+                    for (uint32_t e = 4 * lane; e < bn; e += 128) {
+                        uint4 v = *reinterpret_cast<const uint4*>(row + e);
+                        if (e + 1 >= bn) v.y = BK_PAD;
+                        if (e + 2 >= bn) v.z = BK_PAD;
+                        if (e + 3 >= bn) v.w = BK_PAD;
+                        const uint32_t at = e < bl0 ? bd0 + e : bd1 + (e - bl0);
+                        if (at < cap) {
+                            *reinterpret_cast<uint4*>(dst + at) = v;
+                        } else {  // bucket full (skewed input): apply here, correctness never depends on capacity
+                            int t = 0;
+                            while (b >= bp.first[t + 1]) ++t;
+                            const uint32_t offs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (offs[k] == BK_PAD) continue;
+                                const uint64_t bin = ((uint64_t)(b - bp.first[t]) << bp.shift) + offs[k];
+                                if (bin >= bp.own_lo[t] && bin < bp.own_hi[t]) {
+                                    slot_insert<KIND, false>(ts.ptr[t], bin);
+                                    ++direct;
+                                } else {
+                                    ++dropped;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            phase ^= 1;
+        }
+    }
+    // what is left of the pieces this CTA took is filled with pad entries (k_apply skips them)
+    if (R) {
+#pragma unroll
+        for (int rr = 0; rr < BK_OWN; ++rr) {
+            const int mine = warp + rr * TILE_THREADS + 8 * lane;
+            if (mine >= nb) continue;
+            const uint32_t cap = __ldg(bp.bcap + mine);
+            uint32_t* dst = bp.bptr[mine];
+            const uint4 pad = make_uint4(BK_PAD, BK_PAD, BK_PAD, BK_PAD);
+            for (uint32_t e = c_pos[rr]; e < c_pos[rr] + c_left[rr] && e < cap; e += 4) *reinterpret_cast<uint4*>(dst + e) = pad;
+            if (c_nxt[rr] != BK_NONE)
+                for (uint32_t e = c_nxt[rr]; e < c_nxt[rr] + R && e < cap; e += 4) *reinterpret_cast<uint4*>(dst + e) = pad;
         }
     }
     if (direct) atomicAdd(bp.n_direct, direct);
@@ -267,13 +382,16 @@ k_apply(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ items
 #pragma unroll
         for (int k = 0; k < AP_PER_THREAD / 4; ++k) {
             uint4 x = __ldcs(v + k * AP_THREADS + threadIdx.x);
-            slot_insert<KIND, false>(tbl, x.x);
-            slot_insert<KIND, false>(tbl, x.y);
-            slot_insert<KIND, false>(tbl, x.z);
-            slot_insert<KIND, false>(tbl, x.w);
+            if (x.x != BK_PAD) slot_insert<KIND, false>(tbl, x.x);
+            if (x.y != BK_PAD) slot_insert<KIND, false>(tbl, x.y);
+            if (x.z != BK_PAD) slot_insert<KIND, false>(tbl, x.z);
+            if (x.w != BK_PAD) slot_insert<KIND, false>(tbl, x.w);
         }
     } else {
-        for (uint32_t e = threadIdx.x; e < n; e += AP_THREADS) slot_insert<KIND, false>(tbl, __ldcs(src + e0 + e));
+        for (uint32_t e = threadIdx.x; e < n; e += AP_THREADS) {
+            uint32_t x = __ldcs(src + e0 + e);
+            if (x != BK_PAD) slot_insert<KIND, false>(tbl, x);
+        }
     }
 }
 

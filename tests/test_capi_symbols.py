@@ -77,3 +77,25 @@ def test_host_cursor_shifter_matches_golden(golden):
         assert (str(back.fw_hash), str(back.rc_hash)) == (exp["fw_head"][1], exp["rc_head"][1])
         f = FwdLemireShifter(K)
         assert str(f.hash_base(seq).value()) == golden["hash_vectors"]["cases"]["K%d_can0" % K]["fw_head"][0]
+
+
+def test_bin_of_arithmetic_is_exact():
+    """The cheap reduction k_bucket uses for big tables equals h % d for every divisor class and edge value."""
+    import random
+    from goetia_b200.csrc_check import bin_of_host, fastmod_host
+    rnd = random.Random(7)
+    ds = [2**28, 2**28 + 1, 2**29 - 3, 999999937, 2**30 + 7, 2**31 - 1, 2**31, 3999999979, 2**32 - 1, 2**32, 2**32 + 1,
+          7999999957, 2**33 - 9, 2**40 + 15, 2**58, 2**28 - 1, 999983, 2**58 + 1]
+    ds += [rnd.randrange(2**28, 2**36) for _ in range(40)]
+    for d in ds:
+        hs = [0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, 2**32 - 1, 2**32, 2**63, 2**64 - 1, 2**64 - 2, (2**64 // d) * d - 1,
+              (2**64 // d) * d % 2**64]
+        hs += [rnd.randrange(2**64) for _ in range(400)]
+        hs += [(k * d + rnd.randrange(-2, 3)) % 2**64 for k in (1, 2, 3, 2**20, 2**31) for _ in range(3)]
+        for h in hs:
+            assert fastmod_host(h, d) == h % d
+            got = bin_of_host(h, d)
+            if d < 2**28 or d > 2**58:
+                assert got is None
+            else:
+                assert got == h % d, (h, d)

@@ -30,7 +30,13 @@ def forced(monkeypatch):
 
 @pytest.mark.parametrize("kind,_n", STORAGES)
 @pytest.mark.parametrize("can,_s", SHIFTERS)
-def test_bucketed_insert_bit_exact(gb, forced, kind, _n, can, _s):
+@pytest.mark.parametrize("pieces", [0, 2])
+def test_bucketed_insert_bit_exact(gb, forced, monkeypatch, kind, _n, can, _s, pieces):
+    # pieces=2: room in the global buckets is taken a piece at a time (holes padded) even though the
+    # store is tiny, so most pieces run past the capacity -- the tables must still be exact
+    monkeypatch.setenv("GT_BUCKET_PIECES", str(pieces))
+    if pieces:
+        forced(slice_log2=14, entries=48 << 20)
     K = [31, 21, 25][kind]
     sizes = gb.get_n_primes_near_x(4, 1_000_000)
     bases, offsets = genome_reads(12000, 150, 30000, seed=100 + kind * 10 + can)
@@ -180,4 +186,25 @@ def test_large_tables_default_policy(gb, monkeypatch):
     for a, b in zip(g.get_raw(), ref.tables()):
         assert a.size == b.size and Port.fnv1a(a) == Port.fnv1a(b)
     assert g.n_occupied() == ref.stats()[1]
+    g.S.close()
+
+
+@pytest.mark.parametrize("x", [2**28 + 1000, 2**29 + 12345, 2**30 + 99, 3_000_000_000, 2**32 + 5000])
+def test_big_table_reducers(gb, monkeypatch, x):
+    """Tables of >= 2^28 slots take the 32-bit-reciprocal reduction (bin_of, rs = 4..0): default knobs,
+    tables compared with the oracle through checksums."""
+    for k in ("GT_BUCKET_FORCE", "GT_SLICE_LOG2_BYTES", "GT_PENDING_ENTRIES", "GT_BUCKET_MIN_KMERS"):
+        monkeypatch.delenv(k, raising=False)
+    monkeypatch.setenv("GT_PENDING_ENTRIES", str(64 << 20))
+    monkeypatch.setenv("GT_BUCKET_FORCE", "1")
+    K = 31
+    sizes = gb.get_n_primes_near_x(2, x)
+    bases, offsets = synth_reads(30000, 150, seed=81)
+    g = make_graph(gb, 0, 1, K, sizes)
+    g.insert_sequences(bases, offsets, mode=0)
+    assert g.S.pending_info()["built"] == 1
+    ref = Port(0, 1, K, sizes)
+    ref.insert_reads(bases, offsets)
+    for a, b in zip(g.get_raw(), ref.tables()):
+        assert a.size == b.size and Port.fnv1a(a) == Port.fnv1a(b)
     g.S.close()
