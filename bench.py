@@ -300,23 +300,7 @@ def main():
 
     # ---- roofline -----------------------------------------------------------------------------------
     peak, peak_src = measured_peak()
-    ins_ms = float(prof_ms[0] + prof_ms[1] + prof_ms[2])
-    algo_bytes = ALGO_BYTES_PER_KMER_PER_TABLE * n_tables
-    achieved = kmers_per_step * args.steps * algo_bytes / (ins_ms / 1e3) / 1e9 if ins_ms > 0 else 0.0
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(args.workload)
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src,
-                "kernel": "k_bucket + k_apply (the two halves of one insert: bucket by table slice, apply per slice)",
-                "algorithmic_bytes_per_kmer": algo_bytes,
-                "kernels": {name: {"launches": int(prof_n[i]), "ms_total": float(prof_ms[i]),
-                                   "ms_per_launch": float(prof_ms[i] / max(1, int(prof_n[i]))),
-                                   "share_of_step": float(prof_ms[i] / ms) if ms > 0 else 0.0}
-                            for i, name in enumerate(("k_bucket", "k_apply", "k_walk")) if prof_n[i]}}
+    roofline = insert_roofline(prof_ms, prof_n, ms, kmers_per_step * args.steps, n_tables, peak, peak_src, args.workload)
 
     # ---- CPU baseline ---------------------------------------------------------------------------------
     cpu = None
@@ -350,6 +334,35 @@ def main():
     }
     print(json.dumps(out))
     return 0
+
+
+def insert_roofline(prof_ms, prof_n, step_ms_total, kmers, n_tables, peak, peak_src, workload):
+    """HBM roofline of the insert.  The table sectors are read-modified-written by k_apply (write-combined
+    path) or k_walk (direct path): that kernel carries the algorithmic 64 B per (k-mer, table); k_bucket only
+    produces its input and runs concurrently with it on the other entry store.  `achieved` is therefore the
+    algorithmic bytes over the dominant kernel's own CUDA-event time; `pipeline_achieved` is the same bytes
+    over the whole timed region (everything included), i.e. value x 256 B."""
+    names = ("k_bucket", "k_apply", "k_walk")
+    algo_bytes = ALGO_BYTES_PER_KMER_PER_TABLE * n_tables
+    dom = 1 if prof_n[1] else 2
+    dom_ms = float(prof_ms[dom])
+    achieved = kmers * algo_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(workload)
+    except Exception:
+        pass
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "peak_source": peak_src, "kernel": names[dom],
+            "algorithmic_bytes_per_kmer": algo_bytes,
+            "pipeline_achieved": kmers * algo_bytes / (step_ms_total / 1e3) / 1e9 if step_ms_total > 0 else 0.0,
+            "note": "k_bucket (producer) and k_apply (table read-modify-write) of consecutive entry stores overlap; "
+                    "achieved = 256 B x k-mers / k_apply event time; pipeline_achieved = the same bytes / whole timed region",
+            "kernels": {name: {"launches": int(prof_n[i]), "ms_total": float(prof_ms[i]),
+                               "ms_per_launch": float(prof_ms[i] / max(1, int(prof_n[i]))),
+                               "share_of_step": float(prof_ms[i] / step_ms_total) if step_ms_total > 0 else 0.0}
+                        for i, name in enumerate(names) if prof_n[i]}}
 
 
 def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_reads):

@@ -68,8 +68,11 @@ SIGNATURES = {
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gt_storage_create_sharded": (C.c_void_p, [C.c_int, u64p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int]),
     "gt_storage_local_range": (C.c_int, [C.c_void_p, C.c_int, u64p, u64p]),
-    "gt_storage_attach_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gt_storage_attach_exchange": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gt_storage_select_store": (C.c_int, [C.c_void_p, C.c_int]),
+    "gt_storage_apply_store": (C.c_int, [C.c_void_p, C.c_int]),
     "gt_set_compute_stream": (C.c_int, [C.c_void_p]),
+    "gt_set_apply_stream": (C.c_int, [C.c_void_p]),
     "gt_launch_count": (C.c_uint64, []),
     "gt_timer_record": (C.c_int, [C.c_int]),
     "gt_timer_elapsed_ms": (C.c_double, [C.c_int, C.c_int]),

@@ -119,7 +119,7 @@ __device__ __forceinline__ void bucket_spill(const TableSet& ts, const ProducePl
 }
 
 template <int KIND, bool CAN, int NT>
-__global__ void __launch_bounds__(TILE_THREADS, 3)
+__global__ void __launch_bounds__(TILE_THREADS, 4)  // <= 64 registers: leaves room for two k_apply CTAs per SM beside three of these
 k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts, const __grid_constant__ ProducePlan bp) {
     extern __shared__ __align__(16) uint64_t smem[];
     const int K = a.K;

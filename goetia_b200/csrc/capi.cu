@@ -94,6 +94,9 @@ struct Context {
     int sms = 0;
     cudaStream_t main = nullptr;      // compute stream (the library's own unless gt_set_compute_stream gave another)
     cudaStream_t own_main = nullptr;
+    cudaStream_t apply = nullptr;     // k_apply of a full entry store runs here while the compute stream fills the other
+    cudaStream_t own_apply = nullptr;
+    bool apply_is_external = false;
     Slot slot[2];
     unsigned long long* d_scratch = nullptr;  // [0] k-mer total, [1] occupied, [2..7] spare
     unsigned long long* h_scratch = nullptr;  // pinned mirror
@@ -181,7 +184,15 @@ extern "C" int gt_init(int device) {
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail("gt_init: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     g_ctx.sms = prop.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&g_ctx.own_main, cudaStreamNonBlocking));
+    {
+        // the producer kernels get the higher priority so that they keep their SM slots while the
+        // (L2-bound, issue-light) apply kernel of the previous store runs next to them
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&g_ctx.own_main, cudaStreamNonBlocking, hi));
+        CU(cudaStreamCreateWithPriority(&g_ctx.own_apply, cudaStreamNonBlocking, lo));
+        g_ctx.apply = g_ctx.own_apply;
+    }
     g_ctx.main = g_ctx.own_main;
     for (auto& s : g_ctx.slot) {
         CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
@@ -957,12 +968,15 @@ extern "C" int gt_storage_local_range(const gt_storage* st, int i, uint64_t* lo,
     return 0;
 }
 
-extern "C" int gt_storage_attach_exchange(gt_storage* st, void* outbox, void* inbox, void* fill_send, void* fill_recv) {
+extern "C" int gt_storage_attach_exchange(gt_storage* st, int which, void* outbox, void* inbox, void* fill_send,
+                                           void* fill_recv) {
     if (ensure_ctx()) return -1;
     if (!st || !st->pend || st->world < 2) return fail("gt_storage_attach_exchange: not a sharded storage");
+    if (which < 0 || which > 1) return fail("gt_storage_attach_exchange: buffer set 0 or 1");
     if (!outbox || !inbox || !fill_send || !fill_recv) return fail("gt_storage_attach_exchange: NULL buffer");
     Pending* p = st->pend;
-    if (p->attached) return fail("gt_storage_attach_exchange: already attached");
+    Pending::Store& S = p->store[which];
+    if (S.built) return fail("gt_storage_attach_exchange: buffer set %d already attached", which);
     const PlanHost& H = p->host;
     const int nb = H.nb, W = st->world, me = st->rank;
     std::vector<int> owned;  // my buckets, increasing b
@@ -972,7 +986,14 @@ extern "C" int gt_storage_attach_exchange(gt_storage* st, void* outbox, void* in
         if (H.owner[b] == me) owned.push_back(b);
     }
     const int n_owned = (int)owned.size();
-    if (pending_alloc_common(st, p, n_owned * W)) return -1;
+    if (!p->attached && pending_alloc_common(st, p, n_owned * W)) return -1;  // allocates set 0's arrays too
+    if (which == 1) {
+        if (cudaMalloc(&S.d_bptr, nb * sizeof(uint32_t*)) != cudaSuccess ||
+            cudaMalloc(&S.d_items, (size_t)n_owned * W * sizeof(ApplyItem)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail("gt_storage_attach_exchange: out of device memory");
+        }
+    }
     // outbox: regions of the peers in rank order (skipping me), then my own region
     std::vector<uint64_t> region_start(W, 0);
     uint64_t off = 0;
@@ -988,7 +1009,7 @@ extern "C" int gt_storage_attach_exchange(gt_storage* st, void* outbox, void* in
     uint32_t* ib = static_cast<uint32_t*>(inbox);
     std::vector<uint32_t*> ptrs(nb);
     for (int b = 0; b < nb; ++b) ptrs[b] = ob + region_start[H.owner[b]] + in_region[b];
-    CU(cudaMemcpy(p->d_bptr, ptrs.data(), nb * sizeof(uint32_t*), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(S.d_bptr, ptrs.data(), nb * sizeof(uint32_t*), cudaMemcpyHostToDevice));
     // apply items: slice-major, then source rank
     std::vector<ApplyItem> items;
     items.reserve((size_t)n_owned * W);
@@ -1002,33 +1023,61 @@ extern "C" int gt_storage_attach_exchange(gt_storage* st, void* outbox, void* in
             items.push_back(ApplyItem{src, fr + (size_t)q * n_owned + j, H.slot0[b], H.cap[b], (uint32_t)H.table[b]});
         }
     }
-    if (pending_set_items(p, items)) return -1;
-    p->d_bfill = static_cast<uint32_t*>(fill_send);
+    if (pending_set_items(p, items, which)) return -1;
+    S.d_bfill = static_cast<uint32_t*>(fill_send);
     p->own_bfill = false;
-    p->plan.bfill = p->d_bfill;
-    CU(cudaMemset(p->d_bfill, 0, (size_t)nb * 4));
+    CU(cudaMemset(S.d_bfill, 0, (size_t)nb * 4));
     p->entries_total = off;
+    S.built = true;
     p->attached = true;
     return 0;
 }
 
-// K2 over this rank's slices: its own buckets plus what the peers sent (fill_recv holds the
-// counts).  Asynchronous on the compute stream; empties this rank's cursors for the next round.
+// A sharded storage can hold two buffer sets so that the exchange of one round overlaps the
+// hashing of the next: choose the set the next inserts bucket into.
+extern "C" int gt_storage_select_store(gt_storage* st, int which) {
+    if (!st || !st->pend || st->world < 2) return fail("gt_storage_select_store: not a sharded storage");
+    if (which < 0 || which > 1 || !st->pend->store[which].built) return fail("gt_storage_select_store: set %d not attached", which);
+    st->pend->cur = which;
+    return 0;
+}
+
+// K2 over this rank's slices for one buffer set: its own buckets plus what the peers sent
+// (fill_recv holds the counts).  Asynchronous on the apply stream (gt_set_apply_stream; the
+// compute stream when none was given); empties this rank's cursors of that set.  The caller
+// orders it after the exchange and before the set is bucketed into again.
+extern "C" int gt_storage_apply_store(gt_storage* st, int which) {
+    if (ensure_ctx()) return -1;
+    if (!st || !st->pend || st->world < 2) return fail("gt_storage_apply_store: not a sharded storage");
+    if (which < 0 || which > 1 || !st->pend->store[which].built) return fail("gt_storage_apply_store: set %d not attached", which);
+    Pending::Store& S = st->pend->store[which];
+    S.pending_kmers = std::max<uint64_t>(S.pending_kmers, 1);  // peers may have sent even if this rank bucketed nothing
+    return store_apply_async(st, which);
+}
+
+// Queue the apply of everything pending without waiting (single-GPU storages; on a sharded
+// storage: buffer set 0, after its exchange).
 extern "C" int gt_storage_apply(gt_storage* st) {
     if (ensure_ctx()) return -1;
     if (!st) return fail("gt_storage_apply: NULL storage");
     if (!st->pend) return 0;
-    if (st->world > 1 && !st->pend->attached) return fail("gt_storage_apply: exchange buffers not attached");
-    if (st->world > 1) st->pend->pending_kmers = std::max<uint64_t>(st->pend->pending_kmers, 1);  // peers may have sent even if we did not
+    if (st->world > 1) return gt_storage_apply_store(st, st->pend->cur);
     return pending_flush_async(st);
 }
 
-// Run this library's kernels on a stream of the caller (e.g. torch's current stream) so that
-// they order with the caller's collectives; NULL restores the library's own stream.
+// Run this library's kernels on streams of the caller (e.g. torch streams) so that they order
+// with the caller's collectives; NULL restores the library's own stream.
 extern "C" int gt_set_compute_stream(void* stream) {
     if (ensure_ctx()) return -1;
     CU(cudaDeviceSynchronize());
     g_ctx.main = stream ? static_cast<cudaStream_t>(stream) : g_ctx.own_main;
+    return 0;
+}
+extern "C" int gt_set_apply_stream(void* stream) {
+    if (ensure_ctx()) return -1;
+    CU(cudaDeviceSynchronize());
+    g_ctx.apply = stream ? static_cast<cudaStream_t>(stream) : g_ctx.own_apply;
+    g_ctx.apply_is_external = stream != nullptr;
     return 0;
 }
 
@@ -1056,7 +1105,7 @@ extern "C" int gt_storage_pending_info(gt_storage* st, uint64_t* info) {
     info[2] = (uint64_t)p->plan.shift;
     info[3] = p->budget_kmers;
     info[4] = p->entries_total;
-    info[5] = p->pending_kmers;
+    info[5] = p->pending_total();
     info[6] = nd[0];
     info[7] = p->total_chunks;
     return 0;

@@ -136,7 +136,7 @@ class ShardedStorage:
         self.stream = torch.cuda.Stream()
         _capi.check(L.gt_set_compute_stream(self.stream.cuda_stream), "gt_set_compute_stream")
         self.x = ShardExchange(self.plan, self.rank, torch, torch.device("cuda", torch.cuda.current_device()), group)
-        _capi.check(L.gt_storage_attach_exchange(self._h, self.x.outbox.data_ptr(), self.x.inbox.data_ptr(),
+        _capi.check(L.gt_storage_attach_exchange(self._h, 0, self.x.outbox.data_ptr(), self.x.inbox.data_ptr(),
                                                  self.x.fill_send.data_ptr(), self.x.fill_recv.data_ptr()),
                     "gt_storage_attach_exchange")
 

@@ -214,10 +214,19 @@ int gt_storage_local_range(const gt_storage* st, int i, uint64_t* lo, uint64_t* 
  *   inbox     [(world-1) * R_me]    one copy of this rank's region per peer, in rank order
  *   fill_send [n_buckets]           entry count of every bucket produced here (bucket order)
  *   fill_recv [world * n_owned]     [q][j] = count rank q produced for this rank's j-th bucket */
-int gt_storage_attach_exchange(gt_storage* st, void* outbox, void* inbox, void* fill_send, void* fill_recv);
-/* Run the library's kernels on a caller-owned CUDA stream (NULL = the library's own), so that
- * they order with the caller's collectives on that stream. */
+int gt_storage_attach_exchange(gt_storage* st, int which, void* outbox, void* inbox, void* fill_send,
+                               void* fill_recv);
+/* Two buffer sets (which = 0, 1) may be attached so that the exchange of one round overlaps
+ * the hashing of the next: gt_storage_select_store picks the set the following inserts bucket
+ * into, gt_storage_apply_store queues k_apply for one set on the apply stream (the caller
+ * orders it after that set's exchange and before the set is bucketed into again). */
+int gt_storage_select_store(gt_storage* st, int which);
+int gt_storage_apply_store(gt_storage* st, int which);
+/* Run the library's kernels on caller-owned CUDA streams (NULL = the library's own), so that
+ * they order with the caller's collectives: the compute stream carries pack / hash / bucket,
+ * the apply stream k_apply. */
 int gt_set_compute_stream(void* stream);
+int gt_set_apply_stream(void* stream);
 
 /* ---- SourmashSketch (sketches/sourmash_sketch.hh:24-82) -------------------------------- */
 /* Sketch(n, K, is_protein=false, dayhoff=false, hp=false, seed, scaled):
