@@ -99,6 +99,7 @@ struct Context {
     bool apply_is_external = false;
     Slot slot[2];
     unsigned long long* d_scratch = nullptr;  // [0] k-mer total, [1] occupied, [2..7] spare
+    DevBuf claim_keys, claim_ords;            // GT_MODE_EXACT claim map (compute stream only)
     unsigned long long* h_scratch = nullptr;  // pinned mirror
 };
 static Context g_ctx;
@@ -468,6 +469,7 @@ static int launch_walk_t(const WalkArgs& a, const TableSet& ts, cudaStream_t s) 
         if (occ < 1) occ = 1;
     }
     uint64_t n_tiles = (a.n_bases + TILE_POS - 1) / TILE_POS;
+    if (a.tile_n) n_tiles = std::min(n_tiles - std::min(n_tiles, a.tile_lo), a.tile_n);
     if (n_tiles == 0) return 0;
     int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)g_ctx.sms * occ);
     {
@@ -746,7 +748,20 @@ extern "C" int gt_batch_status(gt_batch* b, int K, uint8_t* status) {
 
 static int check_mode(const char* who, int mode) {
     if (mode != GT_MODE_BLIND && mode != GT_MODE_FAST && mode != GT_MODE_EXACT) return fail("%s: unknown mode %d", who, mode);
-    if (mode == GT_MODE_EXACT) return fail("%s: GT_MODE_EXACT is not available in this build", who);
+    return 0;
+}
+
+// GT_MODE_EXACT claim map for up to `claims` posts, emptied on stream s (kernels.cuh, ClaimMap).
+static uint64_t exact_log2_cap() { return std::min<uint64_t>(32, std::max<uint64_t>(10, env_u64("GT_EXACT_LOG2_CAP", 27))); }
+static int exact_map(uint64_t claims, cudaStream_t s, ClaimMap& m) {
+    uint64_t cap = 1024;
+    while (cap < 2 * claims) cap <<= 1;
+    if (g_ctx.claim_keys.reserve(cap * 8, s) || g_ctx.claim_ords.reserve(cap * 4, s)) return -1;
+    CU(cudaMemsetAsync(g_ctx.claim_keys.p, 0xFF, cap * 8, s));
+    CU(cudaMemsetAsync(g_ctx.claim_ords.p, 0xFF, cap * 4, s));
+    m.keys = g_ctx.claim_keys.as<unsigned long long>();
+    m.ords = g_ctx.claim_ords.as<uint32_t>();
+    m.mask = cap - 1;
     return 0;
 }
 
@@ -756,7 +771,20 @@ static int launch_insert(gt_storage* st, int shifter, const gt_batch& b, int K, 
     a.n_unique = st->d_n_unique;
     a.n_new = d_n_new;
     if (mode == GT_MODE_BLIND) return launch_walk_kind<OP_INSERT, false>(shifter, a, st->ts, s);
-    return launch_walk_kind<OP_INSERT, true>(shifter, a, st->ts, s);
+    if (mode == GT_MODE_FAST) return launch_walk_kind<OP_INSERT, true>(shifter, a, st->ts, s);
+    // GT_MODE_EXACT: ranges of tiles in serial order, each claimed (pass 1) and then inserted (pass 2);
+    // a range is as long as the claim map allows (every k-mer may post one claim per table)
+    const uint64_t n_tiles = (b.n_bases + TILE_POS - 1) / TILE_POS;
+    const uint64_t per = std::max<uint64_t>(1, ((1ull << exact_log2_cap()) / 2) / ((uint64_t)TILE_POS * st->n));
+    for (uint64_t t0 = 0; t0 < n_tiles; t0 += per) {
+        a.tile_lo = t0;
+        a.tile_n = std::min(per, n_tiles - t0);
+        const uint64_t positions = std::min<uint64_t>(a.tile_n * TILE_POS, b.n_bases - t0 * TILE_POS);
+        if (exact_map(positions * st->n, s, a.claims)) return -1;
+        if (launch_walk_kind<OP_CLAIM, false>(shifter, a, st->ts, s)) return -1;
+        if (launch_walk_kind<OP_INSERT_EXACT, false>(shifter, a, st->ts, s)) return -1;
+    }
+    return 0;
 }
 
 extern "C" int64_t gt_insert_batch(gt_storage* st, int shifter, int K, gt_batch* b, int mode, void* stream) {
@@ -848,6 +876,14 @@ extern "C" int64_t gt_insert_sequences(gt_storage* st, int shifter, int K, const
             if (bucket_insert(st, shifter, view, K, chunk_kmers)) return -1;
             CU(cudaEventRecord(sl.consumed, g_ctx.main));
             sl.consumed_pending = true;
+        } else if (mode == GT_MODE_EXACT) {
+            // serial semantics: the chunks' inserts run one after the other on the compute stream
+            // (the slot streams only stage and pack), sharing one claim map
+            CU(cudaEventRecord(sl.packed, s));
+            CU(cudaStreamWaitEvent(g_ctx.main, sl.packed, 0));
+            if (launch_insert(st, shifter, view, K, mode, d_n_new, g_ctx.main)) return -1;
+            CU(cudaEventRecord(sl.consumed, g_ctx.main));
+            CU(cudaStreamWaitEvent(s, sl.consumed, 0));
         } else if (launch_insert(st, shifter, view, K, mode, d_n_new, s)) {
             return -1;
         }
@@ -1288,6 +1324,25 @@ static void launch_insert_hashes_t(const gt_storage* st, const uint64_t* d_h, ui
     else k_insert_hashes<KIND, TRACK, 0><<<grid, 256, 0, s>>>(d_h, n, st->ts, d_new, st->d_n_unique); ++g_launches;
 }
 
+template <int KIND, int NT>
+static int launch_insert_hashes_exact_t(const gt_storage* st, const uint64_t* d_h, uint64_t n, uint8_t* d_new, const ClaimMap& cm,
+                                        cudaStream_t s) {
+    int grid = grid_for(n, 256 * 4, 8);
+    k_claim_hashes<KIND, NT><<<grid, 256, 0, s>>>(d_h, n, st->ts, cm); ++g_launches;
+    k_insert_hashes_exact<KIND, NT><<<grid, 256, 0, s>>>(d_h, n, st->ts, cm, d_new, st->d_n_unique); ++g_launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+static int launch_insert_hashes_exact(const gt_storage* st, const uint64_t* d_h, uint64_t n, uint8_t* d_new, const ClaimMap& cm,
+                                      cudaStream_t s) {
+    const bool four = st->n == 4;
+    switch (st->kind) {
+        case 0: return four ? launch_insert_hashes_exact_t<0, 4>(st, d_h, n, d_new, cm, s) : launch_insert_hashes_exact_t<0, 0>(st, d_h, n, d_new, cm, s);
+        case 1: return four ? launch_insert_hashes_exact_t<1, 4>(st, d_h, n, d_new, cm, s) : launch_insert_hashes_exact_t<1, 0>(st, d_h, n, d_new, cm, s);
+        default: return four ? launch_insert_hashes_exact_t<2, 4>(st, d_h, n, d_new, cm, s) : launch_insert_hashes_exact_t<2, 0>(st, d_h, n, d_new, cm, s);
+    }
+}
+
 extern "C" int gt_insert_hashes(gt_storage* st, const uint64_t* hashes, uint64_t n, int mode, uint8_t* is_new) {
     if (ensure_ctx()) return -1;
     if (!st || (n && !hashes)) return fail("gt_insert_hashes: NULL argument");
@@ -1307,6 +1362,20 @@ extern "C" int gt_insert_hashes(gt_storage* st, const uint64_t* hashes, uint64_t
         uint8_t* d_new = is_new ? sl.out8.as<uint8_t>() : nullptr;
         const uint64_t* d_h = sl.out64a.as<uint64_t>();
         bool track = mode != GT_MODE_BLIND;
+        if (mode == GT_MODE_EXACT) {
+            // chunks in order on the compute stream, each claimed then inserted (see launch_insert)
+            CU(cudaEventRecord(sl.packed, s));
+            CU(cudaStreamWaitEvent(g_ctx.main, sl.packed, 0));
+            const uint64_t per = std::max<uint64_t>(1, ((1ull << exact_log2_cap()) / 2) / (uint64_t)st->n);
+            for (uint64_t j0 = 0; j0 < m; j0 += per) {
+                const uint64_t mm = std::min(per, m - j0);
+                ClaimMap cm;
+                if (exact_map(mm * st->n, g_ctx.main, cm)) return -1;
+                if (launch_insert_hashes_exact(st, d_h + j0, mm, d_new ? d_new + j0 : nullptr, cm, g_ctx.main)) return -1;
+            }
+            CU(cudaEventRecord(sl.consumed, g_ctx.main));
+            CU(cudaStreamWaitEvent(s, sl.consumed, 0));
+        } else
         switch (st->kind * 2 + (track ? 1 : 0)) {
             case 0: launch_insert_hashes_t<0, false>(st, d_h, m, d_new, s); break;
             case 1: launch_insert_hashes_t<0, true>(st, d_h, m, d_new, s); break;

@@ -167,6 +167,77 @@ __device__ __forceinline__ uint32_t storage_query(const TableSet& ts, uint64_t h
 }
 
 // ------------------------------------------------------------------------------------------
+// GT_MODE_EXACT: the serial "first toucher" rule.  The reference inserts
+// k-mers one at a time; k-mer j is new iff some table's slot is still zero when j arrives, i.e.
+// the slot was zero before this launch AND no earlier k-mer of the launch touches it.  Two
+// passes over the same positions reproduce that for any interleaving of threads:
+//   pass 1 (OP_CLAIM)        every k-mer whose slot (t, bin) is zero posts its serial ordinal
+//                            into a claim map keyed by (t, bin); the map keeps the minimum;
+//   pass 2 (OP_INSERT_EXACT) a k-mer is new iff it holds the winning claim of one of its
+//                            slots; then the slots are updated (blind).  Pass 2 never reads a
+//                            table, so its updates cannot disturb another thread's decision.
+// The claim map is an open-addressed table in HBM: keys by CAS, ordinals by atomicMin.
+// ------------------------------------------------------------------------------------------
+struct ClaimMap {
+    unsigned long long* keys;  // CLAIM_EMPTY when free
+    uint32_t* ords;            // 0xFFFFFFFF when free
+    uint64_t mask;             // capacity - 1 (capacity is a power of two >= 2 x claims)
+};
+constexpr unsigned long long CLAIM_EMPTY = ~0ull;
+
+__device__ __forceinline__ uint64_t claim_key(int table, uint64_t bin) { return (bin << 5) | (uint64_t)table; }  // MAX_TABLES == 32
+__device__ __forceinline__ uint64_t claim_mix(uint64_t k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return k;
+}
+__device__ __forceinline__ void claim_post(const ClaimMap& m, uint64_t key, uint32_t ord) {
+    uint64_t s = claim_mix(key) & m.mask;
+    while (true) {
+        unsigned long long cur = m.keys[s];
+        if (cur == CLAIM_EMPTY) cur = atomicCAS(m.keys + s, CLAIM_EMPTY, (unsigned long long)key);
+        if (cur == CLAIM_EMPTY || cur == key) {
+            atomicMin(m.ords + s, ord);
+            return;
+        }
+        s = (s + 1) & m.mask;
+    }
+}
+// ordinal holding the claim of `key`, or 0xFFFFFFFF when nobody claimed it
+__device__ __forceinline__ uint32_t claim_winner(const ClaimMap& m, uint64_t key) {
+    uint64_t s = claim_mix(key) & m.mask;
+    while (true) {
+        unsigned long long cur = m.keys[s];
+        if (cur == key) return m.ords[s];
+        if (cur == CLAIM_EMPTY) return 0xFFFFFFFFu;
+        s = (s + 1) & m.mask;
+    }
+}
+
+// pass 1 for one k-mer
+template <int KIND, int NT>
+__device__ __forceinline__ void storage_claim(const TableSet& ts, const ClaimMap& m, uint64_t h, uint32_t ord) {
+    const int nt = NT > 0 ? NT : ts.n;
+#pragma unroll
+    for (int i = 0; i < nt; ++i) {
+        const uint64_t bin = fastmod_u64(h, ts.size[i], ts.magic[i]);
+        if (slot_query<KIND>(ts.ptr[i], bin) == 0) claim_post(m, claim_key(i, bin), ord);
+    }
+}
+// pass 2 for one k-mer: Storage::insert with the serial is_new
+template <int KIND, int NT>
+__device__ __forceinline__ bool storage_insert_exact(const TableSet& ts, const ClaimMap& m, uint64_t h, uint32_t ord) {
+    const int nt = NT > 0 ? NT : ts.n;
+    bool is_new = false;
+#pragma unroll
+    for (int i = 0; i < nt; ++i) {
+        const uint64_t bin = fastmod_u64(h, ts.size[i], ts.magic[i]);
+        is_new |= claim_winner(m, claim_key(i, bin)) == ord;
+        slot_insert<KIND, false>(ts.ptr[i], bin);
+    }
+    return is_new;
+}
+
+// ------------------------------------------------------------------------------------------
 // K0: validate + 2-bit pack.  One thread per output word (32 bases = 2 x 16 B loads).
 // Folds a/c/g/t to upper case exactly as DNA_SIMPLE::_validate (sequences/alphabets.hh:112-130);
 // any other byte flags its read GT_READ_INVALID (the parser would skip it:
@@ -367,9 +438,10 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_final(const uint64_t* __res
 // rollinghashshifter.hh:203-208).  Windows that cross a read boundary, or lie in a skipped
 // read, are hashed (the roll must continue) but not used.
 //
-// OP: 0 insert, 1 query -> counts, 2 hash -> fw/rc out, 3 median hits (count >= cutoff per read)
+// OP: 0 insert, 1 query -> counts, 2 hash -> fw/rc out, 3 median hits (count >= cutoff per read),
+//     4 / 5 the two passes of GT_MODE_EXACT over the tiles [tile_lo, tile_lo + tile_n)
 // ------------------------------------------------------------------------------------------
-enum { OP_INSERT = 0, OP_QUERY = 1, OP_HASH = 2, OP_MEDIAN = 3 };
+enum { OP_INSERT = 0, OP_QUERY = 1, OP_HASH = 2, OP_MEDIAN = 3, OP_CLAIM = 4, OP_INSERT_EXACT = 5 };
 
 struct WalkArgs {
     const uint64_t* words;     // packed bases
@@ -390,6 +462,9 @@ struct WalkArgs {
     uint32_t cutoff;               // OP_MEDIAN
     unsigned long long* n_unique;  // OP_INSERT tracked
     uint64_t* n_new;               // OP_INSERT tracked, per read (optional)
+    // GT_MODE_EXACT: tile range of this launch (tile_n == 0: all tiles); ordinal = position - tile_lo * TILE_POS
+    uint64_t tile_lo, tile_n;
+    ClaimMap claims;
 };
 
 template <int OP, int KIND, bool CAN, bool TRACK, int NT>
@@ -407,10 +482,12 @@ k_walk(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts) 
         tab[tid] = make_ulonglong2(lemire_T(tid), rotl64(lemire_T(3 - tid), (unsigned)K));
         tab[4 + tid] = make_ulonglong2(rotl64(lemire_T(tid), (unsigned)K), lemire_T(3 - tid));
     }
-    const uint64_t n_tiles = (a.n_bases + TILE_POS - 1) / TILE_POS;
+    uint64_t n_tiles = (a.n_bases + TILE_POS - 1) / TILE_POS;
+    if (a.tile_n && a.tile_lo + a.tile_n < n_tiles) n_tiles = a.tile_lo + a.tile_n;
     unsigned long long block_new = 0;
+    constexpr bool COUNT_NEW = (OP == OP_INSERT && TRACK) || OP == OP_INSERT_EXACT;
 
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (uint64_t tile = a.tile_lo + blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         __syncthreads();  // previous tile's smem fully consumed (and tab visible)
         const uint64_t w0 = tile * TILE_THREADS;
         // stage: 16 B vector loads of the packed words (2 words per load)
@@ -479,7 +556,7 @@ k_walk(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts) 
                     if (CAN) rc = rotr1(rc ^ ti.y ^ to.y);
                 }
                 if (p >= rend) {
-                    if ((OP == OP_MEDIAN || (OP == OP_INSERT && TRACK)) && acc) {
+                    if ((OP == OP_MEDIAN || COUNT_NEW) && acc) {
                         if (OP == OP_MEDIAN) atomicAdd(a.hits + r, acc);
                         else if (a.n_new) atomicAdd((unsigned long long*)(a.n_new + r), (unsigned long long)acc);
                         acc = 0;
@@ -496,6 +573,11 @@ k_walk(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts) 
                     if constexpr (OP == OP_INSERT) {
                         bool nw = storage_insert<KIND, TRACK, NT>(ts, h);
                         if (TRACK) acc += nw, block_new += nw;
+                    } else if constexpr (OP == OP_CLAIM) {
+                        storage_claim<KIND, NT>(ts, a.claims, h, (uint32_t)(p - a.tile_lo * TILE_POS));
+                    } else if constexpr (OP == OP_INSERT_EXACT) {
+                        bool nw = storage_insert_exact<KIND, NT>(ts, a.claims, h, (uint32_t)(p - a.tile_lo * TILE_POS));
+                        acc += nw, block_new += nw;
                     } else if constexpr (OP == OP_QUERY) {
                         a.counts[a.koff[r] + (p - rstart)] = (int16_t)storage_query<KIND, NT>(ts, h);
                     } else if constexpr (OP == OP_HASH) {
@@ -507,13 +589,13 @@ k_walk(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts) 
                     }
                 }
             }
-            if ((OP == OP_MEDIAN || (OP == OP_INSERT && TRACK)) && acc) {
+            if ((OP == OP_MEDIAN || COUNT_NEW) && acc) {
                 if (OP == OP_MEDIAN) atomicAdd(a.hits + r, acc);
                 else if (a.n_new) atomicAdd((unsigned long long*)(a.n_new + r), (unsigned long long)acc);
             }
         }
     }
-    if constexpr (OP == OP_INSERT && TRACK) {
+    if constexpr (COUNT_NEW) {
         for (int o = 16; o; o >>= 1) block_new += __shfl_down_sync(0xffffffffu, block_new, o);
         if ((tid & 31) == 0 && block_new) atomicAdd(a.n_unique, block_new);
     }
@@ -550,6 +632,27 @@ __global__ void __launch_bounds__(256) k_insert_hashes(const uint64_t* __restric
         for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
         if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_unique, mine);
     }
+}
+
+// GT_MODE_EXACT over a hash vector: ordinal = index in the launch (see storage_claim).
+template <int KIND, int NT>
+__global__ void __launch_bounds__(256) k_claim_hashes(const uint64_t* __restrict__ hashes, uint64_t n,
+                                                       const __grid_constant__ TableSet ts, const ClaimMap m) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        storage_claim<KIND, NT>(ts, m, hashes[i], (uint32_t)i);
+}
+template <int KIND, int NT>
+__global__ void __launch_bounds__(256) k_insert_hashes_exact(const uint64_t* __restrict__ hashes, uint64_t n,
+                                                              const __grid_constant__ TableSet ts, const ClaimMap m,
+                                                              uint8_t* __restrict__ is_new, unsigned long long* n_unique) {
+    unsigned long long mine = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        bool nw = storage_insert_exact<KIND, NT>(ts, m, hashes[i], (uint32_t)i);
+        if (is_new) is_new[i] = nw;
+        mine += nw;
+    }
+    for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_unique, mine);
 }
 
 template <int KIND, int NT>

@@ -35,7 +35,7 @@ class dBG:
             cls._specialisations[key] = type(name, (dBG,), {"storage_type": storage_t, "shifter_type": shifter_t})
         return cls._specialisations[key]
 
-    def __init__(self, storage, hasher_or_K, mode=MODE_FAST):
+    def __init__(self, storage, hasher_or_K, mode=MODE_EXACT):
         self.S = storage
         if isinstance(hasher_or_K, int):
             if self.shifter_type is None:

@@ -143,7 +143,7 @@ class _Storage:
         return dict(zip(keys, (int(v) for v in a)))
 
     # -- single-hash members (one launch each; the batch members are the fast path) ---------
-    def insert(self, khash, mode=_capi.MODE_FAST):
+    def insert(self, khash, mode=_capi.MODE_EXACT):
         return bool(self.insert_many([_hash_value(khash)], mode=mode)[0])
 
     def query(self, khash):
@@ -157,7 +157,7 @@ class _Storage:
         return self.query(khash)
 
     # -- batch members -----------------------------------------------------------------------
-    def insert_many(self, hashes, mode=_capi.MODE_FAST, want_new=True):
+    def insert_many(self, hashes, mode=_capi.MODE_EXACT, want_new=True):
         hs = np.ascontiguousarray(hashes, dtype=np.uint64)
         want_new = want_new and mode != _capi.MODE_BLIND
         is_new = np.zeros(max(hs.size, 1), dtype=np.uint8) if want_new else None
