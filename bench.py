@@ -50,6 +50,9 @@ WORKLOADS = {
            "C2: dBG<ByteStorage,CanLemireShifter> K=21, ByteStorage(4e9,4), 20M x 150bp synthetic reads (insert)"),
     "c5": (2, 25, int(8e9), 4, 1_000_000, 10_000, 46,
            "C5: dBG<NibbleStorage,CanLemireShifter> K=25, NibbleStorage(8e9,4), 1M x 10kb synthetic reads"),
+    # sketch workload (kind -1): not the headline metric; `--workload c4` reports k-mers sketched per second
+    "c4": (-1, 31, 1000, 0, 100_000_000, 150, 45,
+           "C4: SourmashSketch K=31 scaled=1000 streaming sketch of 100M x 150bp synthetic reads"),
 }
 SUB_BATCH_BASES = 900_000_000  # reads are fed to the library in sub-batches of about this many bases
 
@@ -210,8 +213,10 @@ def main():
     dev = torch.device("cuda", local_rank)
     gb.init(local_rank)
     L = _capi.lib()
-    sizes = gb.get_n_primes_near_x(n_tables, x)
+    sizes = gb.get_n_primes_near_x(n_tables, x) if kind >= 0 else []
 
+    if kind < 0:
+        return sketch_arm(args, rank, world, local_rank, torch, gb, _capi)
     if world > 1:
         return multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_reads)
 
@@ -506,9 +511,109 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
     return 0
 
 
+def sketch_arm(args, rank, world, local_rank, torch, gb, _capi):
+    """`--workload c4`: every rank sketches its shard of the reads (k_sketch), then the hash sets are
+    united (all-gather + add_hashes) -- exact because a sketch is a set.  Reported in k-mers sketched/s."""
+    _, K, scaled, _, total_reads, read_len, seed, desc = WORKLOADS["c4"]
+    if args.reads:
+        total_reads = args.reads
+    L = _capi.lib()
+    dev = torch.device("cuda", local_rank)
+    kpr = read_len - K + 1
+    reads_rank = total_reads // world + (1 if rank < total_reads % world else 0)
+    reads_per_sub = max(1, min(reads_rank, SUB_BATCH_BASES // read_len))
+    subs, r = [], 0
+    while r < reads_rank:
+        n = min(reads_per_sub, reads_rank - r)
+        subs.append((synth_reads_device(torch, n, read_len, seed + 1000 * len(subs) + 100000 * rank, dev), n))
+        r += n
+    offs = torch.arange(reads_per_sub + 1, dtype=torch.int64, device=dev) * read_len
+    torch.cuda.synchronize()
+    sk = gb.SourmashSketch.Sketch(0, K, False, False, False, 42, scaled)
+
+    def step():
+        nk = 0
+        for b, n in subs:
+            nk += sk.insert_sequences_dev(b.data_ptr(), offs.data_ptr(), n, n * read_len)
+        if world > 1:
+            sk.allgather_merge()
+        return nk
+
+    if world > 1:
+        import torch.distributed as dist
+    for _ in range(args.warmup):
+        assert step() == reads_rank * kpr
+    L.gt_synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = L.gt_launch_count()
+    t0 = time.perf_counter()
+    _capi.check(L.gt_timer_record(0), "gt_timer_record")
+    for _ in range(args.steps):
+        step()
+    _capi.check(L.gt_timer_record(1), "gt_timer_record")
+    ms_dev = L.gt_timer_elapsed_ms(0, 1)
+    L.gt_synchronize()
+    ms_wall = (time.perf_counter() - t0) * 1e3
+    ms = max(ms_dev, ms_wall) if world > 1 else ms_dev  # the union's collectives are not on the library stream
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    launches = int(L.gt_launch_count() - launches0)
+    clocks = sampler.stop()
+    n_mins = sk.size()
+    kmers_per_step = total_reads * kpr
+    value = kmers_per_step * args.steps / (ms / 1e3)
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle.binding import PortSketch
+        nb = min(reads_rank, 150_000)
+        cb = subs[0][0][:nb * read_len].cpu().numpy()
+        co = np.arange(nb + 1, dtype=np.uint64) * np.uint64(read_len)
+        o = PortSketch(0, K, 42, scaled=scaled)
+        nk, secs = o.add_reads(cb, co)
+        cpu = {"value": nk / secs, "unit": "k-mers/s", "cores": 1, "kind": "port",
+               "sample": "%d reads (%d k-mers) of the same set through the plain-C restatement of "
+                         "KmerMinHash::add_sequence (libsourmash is absent: parity unpinned), %.1f s" % (nb, nk, secs)}
+        sub = gb.SourmashSketch.Sketch(0, K, False, False, False, 42, scaled)
+        sub.insert_sequences(cb, co)
+        check = {"prefix_hash_set_equals_oracle": bool(np.array_equal(sub.mins(), o.mins())), "n_mins": n_mins}
+    else:
+        check = {"n_mins": n_mins}
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        in_bytes = total_reads * read_len * args.steps  # ASCII read once by k_pack; packed words re-read by k_sketch
+        out = {"metric": "k-mers sketched/sec (device-timed)", "value": value, "unit": "k-mers/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+               "config": {"workload": desc if not args.reads else desc + " [reads overridden: %d]" % total_reads, "K": K,
+                          "scaled": scaled, "reads": total_reads, "read_len": read_len, "kmers_per_step": kmers_per_step,
+                          "seed": seed, "l2": "inputs larger than L2 (%.1f GB of reads per rank)" % (reads_rank * read_len / 1e9),
+                          "parallelism": "reads sharded over %d rank(s); hash sets united by all-gather" % world},
+               "clocks": clocks, "e2e": None, "gpu_launches": launches,
+               "roofline": {"bound": "hbm", "achieved": in_bytes * 1.25 / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                            "frac": in_bytes * 1.25 / (ms / 1e3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                            "kernel": "k_sketch",
+                            "note": "integer-ALU bound (MurmurHash3_x64_128 per window), not HBM bound: 1.25 B/base "
+                                    "algorithmic (ASCII in + 2-bit words out + words in) is far below the HBM roof"},
+               "cpu_baseline": cpu, "check": check}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def reference_arm(args, rank, world, kind, K, x, n_tables, total_reads, read_len, seed, desc):
     """--impl reference: the reference's own CPU implementation of the path on the host cores."""
     if rank != 0:
+        return 0
+    if kind < 0:
+        print(json.dumps({"impl": "reference", "unavailable": "the sketch arithmetic lives in libsourmash (absent); "
+                                                             "see cpu_baseline of --workload c4"}))
         return 0
     from oracle import binding
     threads = os.cpu_count() or 1

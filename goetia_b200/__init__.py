@@ -11,5 +11,6 @@ from ._capi import GoetiaB200Error, init, MODE_BLIND, MODE_FAST, MODE_EXACT  # n
 from .hashing import FwdLemireShifter, CanLemireShifter, Hash, Canonical  # noqa: F401
 from .storage import BitStorage, ByteStorage, NibbleStorage, get_n_primes_near_x  # noqa: F401
 from .dbg import dBG  # noqa: F401
+from .sketch import SourmashSketch  # noqa: F401
 
 __version__ = "0.1.0"

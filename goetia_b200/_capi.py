@@ -86,6 +86,9 @@ SIGNATURES = {
     "gt_sketch_merge": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gt_sketch_size": (C.c_int64, [C.c_void_p]),
     "gt_sketch_mins": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "gt_sketch_add_sequences_dev": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
+    "gt_sketch_count_common": (C.c_int64, [C.c_void_p, C.c_void_p]),
+    "gt_sketch_reset": (C.c_int, [C.c_void_p]),
 }
 
 

@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(256) k_kmer_counts(const uint64_t* __restrict_
     for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n_reads;
          r += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t len = offsets[r + 1] - offsets[r];
-        uint8_t st = flags[r] & READ_INVALID;
+        uint8_t st = flags ? (flags[r] & READ_INVALID) : 0;
         if (len < (uint64_t)K) st |= READ_SHORT;
         uint64_t c = st ? 0 : len - (uint64_t)K + 1;
         if (kcount) kcount[r] = c;

@@ -238,12 +238,20 @@ void gt_sketch_destroy(gt_sketch* sk);
  * a byte outside ACGTacgt are skipped.  Returns sum of len-K+1 over reads with len >= K. */
 int64_t gt_sketch_add_sequences(gt_sketch* sk, const char* bases, const uint64_t* offsets,
                                 uint64_t n_reads);
+/* Same for reads already resident in HBM (ASCII d_bases, uint64 d_offsets starting at 0): pack + sketch on the
+ * library's compute stream; one 8-byte read-back. */
+int64_t gt_sketch_add_sequences_dev(gt_sketch* sk, const void* d_bases, const void* d_offsets, uint64_t n_reads,
+                                    uint64_t n_bases);
 /* MinHash::add_hash / merge (sourmash.hpp:80, :97) */
 int gt_sketch_add_hashes(gt_sketch* sk, const uint64_t* hashes, uint64_t n);
 int gt_sketch_merge(gt_sketch* dst, gt_sketch* src);
 /* MinHash::size / mins (sourmash.hpp:116, :151-157): ascending, duplicate-free. */
 int64_t gt_sketch_size(gt_sketch* sk);
 int64_t gt_sketch_mins(gt_sketch* sk, uint64_t* out, uint64_t capacity);
+/* MinHash::count_common (sourmash.hpp:102-106): |A n B| of two sketches with equal parameters. */
+int64_t gt_sketch_count_common(gt_sketch* a, gt_sketch* b);
+/* Empty the sketch (parameters kept). */
+int gt_sketch_reset(gt_sketch* sk);
 
 #ifdef __cplusplus
 }

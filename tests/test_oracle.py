@@ -221,6 +221,13 @@ def test_sketch_restatement_properties():
                    for i in range(len(seq) - K + 1)})
     assert skn.mins().tolist() == allh[:50]
     assert Port.max_hash_from_scaled(1000) == 18446744073709552
+    # upstream sourmash's own known answer (tests/test__minhash.py::test_basic_dna): pins canonical choice +
+    # murmur seed 42 + "first 64 bits" + bottom-k for the restatement
+    kat = PortSketch(1, 4, 42, scaled=0)
+    kat.insert_sequence("ATGC")
+    assert kat.mins().tolist() == [12415348535738636339]
+    kat.insert_sequence("GCAT")
+    assert kat.mins().tolist() == [12415348535738636339]
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
