@@ -69,6 +69,13 @@ SIGNATURES = {
     "gt_storage_create_sharded": (C.c_void_p, [C.c_int, u64p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int]),
     "gt_storage_local_range": (C.c_int, [C.c_void_p, C.c_int, u64p, u64p]),
     "gt_storage_attach_exchange": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gt_peer_alloc": (C.c_void_p, [C.c_uint64]),
+    "gt_peer_free": (C.c_int, [C.c_void_p]),
+    "gt_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gt_peer_open": (C.c_void_p, [C.c_void_p]),
+    "gt_peer_close": (C.c_int, [C.c_void_p]),
+    "gt_storage_attach_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gt_query_hashes_local_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "gt_storage_select_store": (C.c_int, [C.c_void_p, C.c_int]),
     "gt_storage_apply_store": (C.c_int, [C.c_void_p, C.c_int]),
     "gt_set_compute_stream": (C.c_int, [C.c_void_p]),
@@ -78,6 +85,13 @@ SIGNATURES = {
     "gt_timer_elapsed_ms": (C.c_double, [C.c_int, C.c_int]),
     "gt_profile_enable": (C.c_int, [C.c_int]),
     "gt_profile_get": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gt_fastx_open": (C.c_void_p, [C.c_char_p, C.c_int, C.c_uint32]),
+    "gt_fastx_close": (None, [C.c_void_p]),
+    "gt_fastx_next_record": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
+    "gt_fastx_next_batch": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
+    "gt_fastx_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gt_insert_fastx": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint64, C.c_void_p]),
     "gt_max_hash_from_scaled": (C.c_uint64, [C.c_uint64]),
     "gt_sketch_create": (C.c_void_p, [C.c_uint32, C.c_int, C.c_uint32, C.c_uint64]),
     "gt_sketch_destroy": (None, [C.c_void_p]),

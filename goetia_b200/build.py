@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "capi.cu")
 DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("kernels.cuh", "sketch.cuh", "sketch_host.inc", "bucket.cuh",
-                                                          "bucket_host.inc")] + [os.path.join(ROOT, "include", "goetia_b200.h")]
+                                                          "bucket_host.inc", "fastx_host.inc")] + [os.path.join(ROOT, "include", "goetia_b200.h")]
 OUT = os.path.join(HERE, "libgoetia_b200.so")
 
 NVCC_FLAGS = [
@@ -24,6 +24,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
     "-shared",
 ]
+LIBS = ["-lz"]  # gz-transparent FASTX front end (the reference links zlib for the same purpose)
 
 
 def nvcc_path():
@@ -43,7 +44,7 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC] + LIBS
     if verbose:
         print(" ".join(cmd))
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -1069,6 +1070,133 @@ extern "C" int gt_storage_attach_exchange(gt_storage* st, int which, void* outbo
     return 0;
 }
 
+// ---- peer-memory transport ---------------------------------------------------------------
+extern "C" void* gt_peer_alloc(uint64_t bytes) {
+    if (ensure_ctx()) return nullptr;
+    CUP(cudaSetDevice(g_ctx.device));
+    void* p = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        fail("gt_peer_alloc: cudaMalloc(%llu) failed: %s", (unsigned long long)bytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    CUP(cudaMemset(p, 0, bytes));
+    return p;
+}
+extern "C" int gt_peer_free(void* ptr) {
+    if (!ptr) return 0;
+    CU(cudaDeviceSynchronize());
+    CU(cudaFree(ptr));
+    return 0;
+}
+extern "C" int gt_peer_export(void* ptr, uint8_t handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    if (ensure_ctx()) return -1;
+    if (!ptr || !handle) return fail("gt_peer_export: NULL argument");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle, &h, 64);
+    return 0;
+}
+extern "C" void* gt_peer_open(const uint8_t handle[64]) {
+    if (ensure_ctx()) return nullptr;
+    if (!handle) { fail("gt_peer_open: NULL handle"); return nullptr; }
+    CUP(cudaSetDevice(g_ctx.device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void* p = nullptr;
+    CUP(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    return p;
+}
+extern "C" int gt_peer_close(void* ptr) {
+    if (!ptr) return 0;
+    CU(cudaDeviceSynchronize());
+    CU(cudaIpcCloseMemHandle(ptr));
+    return 0;
+}
+
+extern "C" int gt_storage_attach_peers(gt_storage* st, int which, void* const* inbox_of_rank, void* fill_send,
+                                        void* fill_recv) {
+    if (ensure_ctx()) return -1;
+    if (!st || !st->pend || st->world < 2) return fail("gt_storage_attach_peers: not a sharded storage");
+    if (which < 0 || which > 1) return fail("gt_storage_attach_peers: buffer set 0 or 1");
+    if (!inbox_of_rank || !fill_send || !fill_recv) return fail("gt_storage_attach_peers: NULL buffer");
+    Pending* p = st->pend;
+    Pending::Store& S = p->store[which];
+    if (S.built) return fail("gt_storage_attach_peers: buffer set %d already attached", which);
+    const PlanHost& H = p->host;
+    const int nb = H.nb, W = st->world, me = st->rank;
+    for (int q = 0; q < W; ++q)
+        if (!inbox_of_rank[q]) return fail("gt_storage_attach_peers: inbox of rank %d is NULL", q);
+    std::vector<int> owned;
+    std::vector<uint64_t> R(W, 0), in_region(nb, 0);
+    for (int b = 0; b < nb; ++b) {
+        in_region[b] = R[H.owner[b]];
+        R[H.owner[b]] += H.cap[b];
+        if (H.owner[b] == me) owned.push_back(b);
+    }
+    const int n_owned = (int)owned.size();
+    if (!p->attached && pending_alloc_common(st, p, n_owned * W)) return -1;
+    if (which == 1) {
+        if (cudaMalloc(&S.d_bptr, nb * sizeof(uint32_t*)) != cudaSuccess ||
+            cudaMalloc(&S.d_items, (size_t)n_owned * W * sizeof(ApplyItem)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail("gt_storage_attach_peers: out of device memory");
+        }
+    }
+    // bucket b, produced here, lands in region `me` of its owner's inbox
+    std::vector<uint32_t*> ptrs(nb);
+    for (int b = 0; b < nb; ++b)
+        ptrs[b] = static_cast<uint32_t*>(inbox_of_rank[H.owner[b]]) + (uint64_t)me * R[H.owner[b]] + in_region[b];
+    CU(cudaMemcpy(S.d_bptr, ptrs.data(), nb * sizeof(uint32_t*), cudaMemcpyHostToDevice));
+    std::vector<ApplyItem> items;
+    items.reserve((size_t)n_owned * W);
+    const uint32_t* fr = static_cast<const uint32_t*>(fill_recv);
+    const uint32_t* mine = static_cast<const uint32_t*>(inbox_of_rank[me]);
+    for (int j = 0; j < n_owned; ++j) {
+        const int b = owned[j];
+        for (int q = 0; q < W; ++q)
+            items.push_back(ApplyItem{mine + (uint64_t)q * R[me] + in_region[b], fr + (size_t)q * n_owned + j, H.slot0[b], H.cap[b],
+                                      (uint32_t)H.table[b]});
+    }
+    if (pending_set_items(p, items, which)) return -1;
+    S.d_bfill = static_cast<uint32_t*>(fill_send);
+    p->own_bfill = false;
+    CU(cudaMemset(S.d_bfill, 0, (size_t)nb * 4));
+    p->entries_total = (uint64_t)W * R[me];
+    S.built = true;
+    p->attached = true;
+    return 0;
+}
+
+extern "C" int gt_query_hashes_local_dev(gt_storage* st, const void* d_hashes, uint64_t n, void* d_counts) {
+    if (ensure_ctx()) return -1;
+    if (!st || (n && (!d_hashes || !d_counts))) return fail("gt_query_hashes_local_dev: NULL argument");
+    if (st->pend && st->pend->pending_total()) return fail("gt_query_hashes_local_dev: updates are pending (exchange and apply first)");
+    if (n == 0) return 0;
+    CU(cudaSetDevice(g_ctx.device));
+    cudaStream_t s = g_ctx.main;
+    if (g_ctx.apply) {  // queries must see every applied update
+        cudaEvent_t& ev = g_ctx.slot[0].packed;
+        CU(cudaEventRecord(ev, g_ctx.apply));
+        CU(cudaStreamWaitEvent(s, ev, 0));
+    }
+    OwnRange own;
+    memset(&own, 0, sizeof own);
+    for (int i = 0; i < st->n; ++i) { own.lo[i] = st->own_lo[i]; own.hi[i] = st->own_hi[i]; }
+    const uint64_t* d_h = static_cast<const uint64_t*>(d_hashes);
+    int16_t* d_c = static_cast<int16_t*>(d_counts);
+    const int grid = grid_for(n, 256 * 4, 8);
+    if (st->kind == 0) k_query_hashes_local<0><<<grid, 256, 0, s>>>(d_h, n, st->ts, own, d_c);
+    else if (st->kind == 1) k_query_hashes_local<1><<<grid, 256, 0, s>>>(d_h, n, st->ts, own, d_c);
+    else k_query_hashes_local<2><<<grid, 256, 0, s>>>(d_h, n, st->ts, own, d_c);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+
 // A sharded storage can hold two buffer sets so that the exchange of one round overlaps the
 // hashing of the next: choose the set the next inserts bucket into.
 extern "C" int gt_storage_select_store(gt_storage* st, int which) {
@@ -1427,3 +1555,4 @@ extern "C" int gt_query_hashes(gt_storage* st, const uint64_t* hashes, uint64_t 
 }
 
 #include "sketch_host.inc"
+#include "fastx_host.inc"

@@ -662,6 +662,28 @@ __global__ void __launch_bounds__(256) k_query_hashes(const uint64_t* __restrict
         counts[i] = (int16_t)storage_query<KIND, NT>(ts, __ldcs(hashes + i));
 }
 
+// Storage::query restricted to the slot ranges [lo_t, hi_t) this rank holds (sharded storage):
+// tables whose slot lies elsewhere contribute the neutral element, so the MIN over all ranks'
+// answers is the reference's AND / min over all tables.
+struct OwnRange { uint64_t lo[MAX_TABLES], hi[MAX_TABLES]; };
+template <int KIND>
+__global__ void __launch_bounds__(256) k_query_hashes_local(const uint64_t* __restrict__ hashes, uint64_t n,
+                                                             const __grid_constant__ TableSet ts,
+                                                             const __grid_constant__ OwnRange own, int16_t* __restrict__ counts) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t h = __ldcs(hashes + i);
+        uint32_t acc = KIND == 0 ? 1u : KIND == 1 ? 255u : 15u;
+        for (int t = 0; t < ts.n; ++t) {
+            const uint64_t bin = fastmod_u64(h, ts.size[t], ts.magic[t]);
+            if (bin >= own.lo[t] && bin < own.hi[t]) {
+                const uint32_t x = slot_query<KIND>(ts.ptr[t], bin);
+                acc = KIND == 0 ? (acc & x) : min(acc, x);
+            }
+        }
+        counts[i] = (int16_t)acc;
+    }
+}
+
 // number of non-zero slots of a table (n_occupied == non-zero slots of table 0, because the
 // reference bumps _occupied_bins exactly when a table-0 slot leaves zero: bitstorage.hh:205-208,
 // bytestorage.cc:71-77, nibblestorage.cc:75-81).

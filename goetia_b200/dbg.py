@@ -161,6 +161,28 @@ class dBG:
     def flush(self):
         self.S.flush()
 
+    def process_fastx(self, parser_or_filename, mode=MODE_BLIND, max_reads=0, strict=False, min_length=0):
+        """FileProcessor<InserterProcessor<dBG>>::process / advance (processors.hh:112-127, 208-229,
+        304-331): stream a FASTX file (or an open FastxParser; ``max_reads`` > 0 stops after that many
+        records, like one ``advance`` interval) into the graph.  Returns (sequences processed, k-mers
+        consumed); parsing of batch n+1 overlaps the GPU work of batch n (gt_insert_fastx)."""
+        import ctypes as C
+        from .parsing import FastxParser, _ERRORS
+        own = not isinstance(parser_or_filename, FastxParser)
+        parser = FastxParser(parser_or_filename, strict, min_length) if own else parser_or_filename
+        try:
+            n_seqs = C.c_uint64(0)
+            nk = _capi.lib().gt_insert_fastx(self.S.handle, self.hasher.shifter_kind, self.K, parser.handle, int(mode),
+                                             int(max_reads), C.byref(n_seqs))
+            if nk < 0:
+                raise _ERRORS.get(int(nk), _capi.GoetiaB200Error)("gt_insert_fastx: " + _capi.last_error())
+            if mode == MODE_BLIND:
+                self.S.flush()
+            return int(n_seqs.value), int(nk)
+        finally:
+            if own:
+                parser.close()
+
     def query_sequences(self, bases, offsets, want_status=False):
         """dBG::query_sequence over a read batch: counts of all k-mers, reads back to back."""
         L = _capi.lib()

@@ -1,0 +1,128 @@
+"""FASTX front end: mirror of goetia's parsing surface over the C ABI (gt_fastx_*).
+
+Reference: ``FastxParser<DNA_SIMPLE>`` (include/goetia/parsing/readers.hh:86-219) over kseq
+(parsing/kseq.h:174-214), ``Record`` (parsing/parsing.hh:26-58) and the exceptions the parser
+raises (parsing/parsing.hh, goetia.hh:140-178).  The parser itself is C++ inside
+libgoetia_b200.so (csrc/fastx_host.inc): a reader thread inflates ahead, records are located with
+memchr, and ``next_batch`` hands whole batches to the device pipeline.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import GoetiaB200Error
+
+
+class NoMoreReadsAvailable(GoetiaB200Error):
+    pass
+
+
+class InvalidRead(GoetiaB200Error):
+    pass
+
+
+class GoetiaFileException(GoetiaB200Error):
+    pass
+
+
+class InvalidCharacterException(GoetiaB200Error):
+    pass
+
+
+_ERRORS = {-2: InvalidRead, -3: GoetiaFileException, -4: InvalidCharacterException, -5: NoMoreReadsAvailable}
+
+
+class Record:
+    """parsing.hh:26-58"""
+    __slots__ = ("name", "sequence", "quality")
+
+    def __init__(self, name="", sequence="", quality=""):
+        self.name, self.sequence, self.quality = name, sequence, quality
+
+    def write_fastx(self, out):
+        if self.quality:
+            out.write("@%s\n%s\n+\n%s\n" % (self.name, self.sequence, self.quality))
+        else:
+            out.write(">%s\n%s\n" % (self.name, self.sequence))
+
+    def __repr__(self):
+        return "<Sequence name=%s seq=%s>" % (self.name, self.sequence)
+
+
+class FastxParser:
+    """FastxParser<DNA_SIMPLE>(infile, strict=False, min_length=0)."""
+
+    def __init__(self, infile, strict=False, min_length=0):
+        L = _capi.load()  # host-only: no GPU needed to parse
+        self._h = L.gt_fastx_open(str(infile).encode(), int(bool(strict)), int(min_length))
+        if not self._h:
+            raise GoetiaFileException(_capi.last_error())
+        self.filename = str(infile)
+
+    @classmethod
+    def build(cls, filename, strict=False, min_length=0):
+        return cls(filename, strict, min_length)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def _raise(self, rc):
+        raise _ERRORS.get(int(rc), GoetiaB200Error)(_capi.last_error())
+
+    def next(self):
+        """std::optional<Record>: a Record, or None for a skipped record / the end of the file."""
+        L = _capi.load()
+        p = [C.c_char_p() for _ in range(3)]
+        n = [C.c_uint64() for _ in range(3)]
+        rc = L.gt_fastx_next_record(self._h, C.byref(p[0]), C.byref(n[0]), C.byref(p[1]), C.byref(n[1]),
+                                    C.byref(p[2]), C.byref(n[2]))
+        if rc < 0:
+            self._raise(rc)
+        if rc == 0:
+            return None
+        s = [C.string_at(p[i], n[i].value).decode("latin-1") if n[i].value else "" for i in range(3)]
+        return Record(s[0], s[1], s[2])
+
+    def __iter__(self):
+        while not self.is_complete():
+            r = self.next()
+            if r is not None:
+                yield r
+
+    def next_batch(self, max_bases=64 << 20, max_reads=None):
+        """(bases uint8, offsets uint64) of the next kept records; offsets.size == 1 at the end of the file."""
+        L = _capi.load()
+        max_reads = int(max_reads) if max_reads else max(1024, max_bases // 32)
+        bases = np.empty(max_bases, dtype=np.uint8)
+        offsets = np.empty(max_reads + 1, dtype=np.uint64)
+        n = L.gt_fastx_next_batch(self._h, bases.ctypes.data, max_bases, offsets.ctypes.data, max_reads)
+        if n < 0:
+            self._raise(n)
+        return bases[:int(offsets[n])], offsets[:n + 1]
+
+    def _stats(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_int()
+        _capi.check(_capi.load().gt_fastx_stats(self._h, C.byref(a), C.byref(b), C.byref(c)), "gt_fastx_stats")
+        return a.value, b.value, bool(c.value)
+
+    def n_parsed(self):
+        return self._stats()[0]
+
+    def n_skipped(self):
+        return self._stats()[1]
+
+    def is_complete(self):
+        return self._stats()[2]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _capi.load().gt_fastx_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -17,6 +17,8 @@ range -- SURVEY.md section 8e).  Per round every rank
 collectives, any torch device / backend) are what the CPU gloo tests exercise; ``ShardedStorage``
 binds them to the CUDA library.
 """
+import ctypes as C
+
 import numpy as np
 
 from . import _capi
@@ -118,47 +120,190 @@ class ShardExchange:
 
 
 class ShardedStorage:
-    """This rank's part of a BitStorage / ByteStorage / NibbleStorage sharded over the process group."""
+    """This rank's part of a BitStorage / ByteStorage / NibbleStorage sharded over the process group.
 
-    def __init__(self, kind, sizes, budget_kmers, group=None, slice_log2_bytes=0):
+    Two transports move the buckets of foreign slices to their owners:
+
+    ``p2p`` (default)  k_bucket stores every run of entries straight into the owner's inbox over
+                       NVLink (peer memory mapped with CUDA IPC, ``gt_storage_attach_peers``): the
+                       transfer is fused with the hashing, run by run.  Only the per-bucket fill
+                       counts travel by collective (one small all-to-all), which doubles as the
+                       "every producer has finished" signal.
+    ``nccl``           k_bucket fills a local outbox; one NCCL all-to-all ships the regions.
+
+    Either way there are two buffer sets and two streams: k_apply of round i (apply stream)
+    overlaps k_bucket of round i+1 into the other set (compute stream).
+    """
+
+    def __init__(self, kind, sizes, budget_kmers, group=None, slice_log2_bytes=0, transport=None):
+        import os
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.group = torch, dist, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.transport = transport or os.environ.get("GT_SHARD_TRANSPORT", "p2p")
+        if self.transport not in ("p2p", "nccl"):
+            raise ValueError("transport must be 'p2p' or 'nccl'")
         L = _capi.lib()
         self.kind = int(kind)
-        self.plan = ShardPlan(kind, sizes, self.world, budget_kmers, slice_log2_bytes)
-        self._sizes = self.plan.sizes
+        self.plan = plan = ShardPlan(kind, sizes, self.world, budget_kmers, slice_log2_bytes)
+        self._sizes = plan.sizes
         self._h = L.gt_storage_create_sharded(self.kind, self._sizes.ctypes.data_as(_capi.u64p), self._sizes.size,
                                               self.rank, self.world, int(budget_kmers), int(slice_log2_bytes))
         if not self._h:
             raise _capi.GoetiaB200Error("gt_storage_create_sharded: " + _capi.last_error())
-        self.stream = torch.cuda.Stream()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
+        self.stream = torch.cuda.Stream(priority=hi)   # pack / hash / bucket (+ the exchange)
+        self.apply_stream = torch.cuda.Stream(priority=lo)
         _capi.check(L.gt_set_compute_stream(self.stream.cuda_stream), "gt_set_compute_stream")
-        self.x = ShardExchange(self.plan, self.rank, torch, torch.device("cuda", torch.cuda.current_device()), group)
-        _capi.check(L.gt_storage_attach_exchange(self._h, 0, self.x.outbox.data_ptr(), self.x.inbox.data_ptr(),
-                                                 self.x.fill_send.data_ptr(), self.x.fill_recv.data_ptr()),
-                    "gt_storage_attach_exchange")
+        _capi.check(L.gt_set_apply_stream(self.apply_stream.cuda_stream), "gt_set_apply_stream")
+        self.cur = 0
+        self._applied = [None, None]   # event: k_apply of the set has finished (its buffers are free again)
+        self._peer_ptrs, self._own_inbox = [], []
+        W, me = self.world, self.rank
+        if self.transport == "nccl":
+            self.sets = [ShardExchange(plan, me, torch, dev, group) for _ in range(2)]
+            for w, x in enumerate(self.sets):
+                _capi.check(L.gt_storage_attach_exchange(self._h, w, x.outbox.data_ptr(), x.inbox.data_ptr(),
+                                                         x.fill_send.data_ptr(), x.fill_recv.data_ptr()),
+                            "gt_storage_attach_exchange")
+            self.x = self.sets[0]
+        else:
+            self._perm = torch.as_tensor(plan.perm, dtype=torch.int64, device=dev)
+            self._fill_in = [plan.n_owned[q] for q in range(W)]
+            self._fill_out = [plan.n_owned[me]] * W
+            self.fill_send, self.fill_recv, self._fx = [], [], []
+            for w in range(2):
+                own = L.gt_peer_alloc(max(16, W * plan.region[me] * 4))
+                if not own:
+                    raise _capi.GoetiaB200Error("gt_peer_alloc: " + _capi.last_error())
+                self._own_inbox.append(own)
+                handle = np.zeros(64, dtype=np.uint8)
+                _capi.check(L.gt_peer_export(own, handle.ctypes.data), "gt_peer_export")
+                mine = torch.from_numpy(handle).to(dev)
+                allh = torch.empty(W * 64, dtype=torch.uint8, device=dev)
+                dist.all_gather_into_tensor(allh, mine, group=group)
+                allh = allh.cpu().numpy().reshape(W, 64)
+                ptrs = (C.c_void_p * W)()
+                for q in range(W):
+                    if q == me:
+                        ptrs[q] = own
+                    else:
+                        hq = np.ascontiguousarray(allh[q])
+                        pq = L.gt_peer_open(hq.ctypes.data)
+                        if not pq:
+                            raise _capi.GoetiaB200Error("gt_peer_open(rank %d): %s" % (q, _capi.last_error()))
+                        self._peer_ptrs.append(pq)
+                        ptrs[q] = pq
+                fs = torch.zeros(max(plan.nb, 1), dtype=torch.int32, device=dev)
+                fr = torch.zeros(max(W * plan.n_owned[me], 1), dtype=torch.int32, device=dev)
+                self.fill_send.append(fs)
+                self.fill_recv.append(fr)
+                self._fx.append(torch.zeros(max(plan.nb, 1), dtype=torch.int32, device=dev))
+                _capi.check(L.gt_storage_attach_peers(self._h, w, ptrs, fs.data_ptr(), fr.data_ptr()),
+                            "gt_storage_attach_peers")
+            torch.cuda.synchronize()
+            dist.barrier(group=group)  # every rank has mapped every inbox before anyone stores into one
 
     @property
     def handle(self):
         return self._h
 
     def bucket_sequences_dev(self, shifter_kind, K, d_bases_ptr, d_offsets_ptr, n_reads, n_bases):
-        """Step 1 of a round: pack + hash + bucket this rank's (device-resident) reads."""
+        """Step 1 of a round: pack + hash + bucket this rank's (device-resident) reads into the
+        current buffer set (p2p: the entries of foreign slices go straight to their owners)."""
+        L = _capi.lib()
         with self.torch.cuda.stream(self.stream):
-            return int(_capi.check(_capi.lib().gt_insert_sequences_dev(self._h, shifter_kind, K, d_bases_ptr, d_offsets_ptr,
-                                                                       n_reads, n_bases, _capi.MODE_BLIND),
+            if self._applied[self.cur] is not None:
+                self.stream.wait_event(self._applied[self.cur])
+            _capi.check(L.gt_storage_select_store(self._h, self.cur), "gt_storage_select_store")
+            return int(_capi.check(L.gt_insert_sequences_dev(self._h, shifter_kind, K, d_bases_ptr, d_offsets_ptr,
+                                                             n_reads, n_bases, _capi.MODE_BLIND),
                                    "gt_insert_sequences_dev"))
 
     def exchange_and_apply(self):
-        """Steps 2 and 3: all-to-all of counts and bucket regions, then apply this rank's slices."""
-        with self.torch.cuda.stream(self.stream):
-            self.x.exchange()
-            _capi.check(_capi.lib().gt_storage_apply(self._h), "gt_storage_apply")
+        """Steps 2 and 3 of a round (collective: every rank calls it once per round): exchange of
+        the current set, k_apply of this rank's slices on the apply stream, switch sets."""
+        torch, dist, plan, w = self.torch, self.dist, self.plan, self.cur
+        with torch.cuda.stream(self.stream):
+            if self.transport == "nccl":
+                self.sets[w].exchange()
+            else:
+                # Peers start storing into my OTHER set as soon as they are past this exchange, so
+                # it must not complete before that set's k_apply has finished here.
+                if self._applied[w ^ 1] is not None:
+                    self.stream.wait_event(self._applied[w ^ 1])
+                torch.index_select(self.fill_send[w][:plan.nb], 0, self._perm, out=self._fx[w][:plan.nb])
+                dist.all_to_all_single(self.fill_recv[w][:plan.world * plan.n_owned[self.rank]], self._fx[w][:plan.nb],
+                                       self._fill_out, self._fill_in, group=self.group)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.apply_stream.wait_event(ev)
+        _capi.check(_capi.lib().gt_storage_apply_store(self._h, w), "gt_storage_apply_store")
+        done = torch.cuda.Event()
+        done.record(self.apply_stream)
+        self._applied[w] = done
+        self.cur = w ^ 1
+
+    def join(self):
+        """Order the compute stream after every k_apply queued so far (no host wait): an event
+        recorded on ``stream`` after this covers the whole round, both streams."""
+        for ev in self._applied:
+            if ev is not None:
+                self.stream.wait_event(ev)
 
     def synchronize(self):
         self.stream.synchronize()
+        self.apply_stream.synchronize()
+
+    # ---- routed queries (SURVEY.md section 8e): every rank answers for the slots it holds ----------
+    def query_hashes(self, hashes):
+        """Storage::query for a vector of hash values (collective; every rank may pass its own,
+        differently sized vector and gets its own answers back): the values are all-gathered, each
+        rank answers for the slots it holds (gt_query_hashes_local_dev) and an all-reduce MIN
+        combines the answers -- AND of bits / min of counters over all tables."""
+        torch, dist = self.torch, self.dist
+        h = np.ascontiguousarray(hashes, dtype=np.uint64)
+        W, dev = self.world, self.device
+        self.synchronize()
+        with torch.cuda.stream(self.stream):
+            n = torch.tensor([h.size], dtype=torch.int64, device=dev)
+            ns = torch.empty(W, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(ns, n, group=self.group)
+            m = int(ns.max().item())
+            if m == 0:
+                return np.zeros(0, dtype=np.int16)
+            mine = torch.zeros(m, dtype=torch.int64, device=dev)
+            if h.size:
+                mine[:h.size] = torch.from_numpy(h.view(np.int64)).to(dev)
+            allh = torch.empty(W * m, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allh, mine, group=self.group)
+            counts = torch.empty(W * m, dtype=torch.int16, device=dev)
+            self.stream.synchronize()
+            _capi.check(_capi.lib().gt_query_hashes_local_dev(self._h, allh.data_ptr(), W * m, counts.data_ptr()),
+                        "gt_query_hashes_local_dev")
+            c32 = counts.to(torch.int32)  # NCCL has no 16-bit integer type
+            dist.all_reduce(c32, op=dist.ReduceOp.MIN, group=self.group)
+            out = c32[self.rank * m:self.rank * m + h.size].to(torch.int16).cpu().numpy()
+        return out
+
+    def query_sequences(self, shifter_kind, K, bases, offsets):
+        """dBG::query_sequence over a host batch against the sharded tables (collective)."""
+        bases, offsets = _capi.as_reads(bases, offsets)
+        n_reads = offsets.size - 1
+        lens = (offsets[1:] - offsets[:-1]).astype(np.int64)
+        cap = int(np.maximum(lens - K + 1, 0).sum())
+        fw = np.empty(max(cap, 1), dtype=np.uint64)
+        rc = np.empty(max(cap, 1), dtype=np.uint64)
+        nk = 0
+        if n_reads:
+            nk = int(_capi.check(_capi.lib().gt_hash_sequences(shifter_kind, K, bases.ctypes.data, offsets.ctypes.data,
+                                                               n_reads, fw.ctypes.data, rc.ctypes.data, None),
+                                 "gt_hash_sequences"))
+        v = np.minimum(fw[:nk], rc[:nk]) if shifter_kind == _capi.SHIFTER_CAN else fw[:nk]
+        return self.query_hashes(v)
 
     def local_range(self, i):
         lo, hi = np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint64)
@@ -169,6 +314,7 @@ class ShardedStorage:
     def local_tables(self):
         """Host copies of this rank's parts; concatenated in rank order they are the reference's tables."""
         L = _capi.lib()
+        self.synchronize()
         out = []
         for i in range(self._sizes.size):
             buf = np.empty(int(L.gt_storage_table_bytes(self._h, i)), dtype=np.uint8)
@@ -178,6 +324,7 @@ class ShardedStorage:
 
     def n_occupied_local(self):
         a = np.zeros(2, dtype=np.uint64)
+        self.synchronize()
         _capi.check(_capi.lib().gt_storage_stats(self._h, a[0:].ctypes.data_as(_capi.u64p),
                                                  a[1:].ctypes.data_as(_capi.u64p)), "gt_storage_stats")
         return int(a[1])
@@ -195,17 +342,38 @@ class ShardedStorage:
         return dict(zip(keys, (int(v) for v in a)))
 
     def reset(self):
+        self.synchronize()
         _capi.check(_capi.lib().gt_storage_reset(self._h), "gt_storage_reset")
 
-    def close(self):
+    def close(self, collective=True):
+        """Collective when the transport is p2p (barriers keep a peer from storing into, or
+        holding a mapping of, memory that is going away)."""
         if getattr(self, "_h", None):
             L = _capi.load()
+            L.gt_synchronize()
+            if self.transport == "p2p" and collective:
+                # nobody may still be storing into a mapping that is about to go away
+                try:
+                    self.dist.barrier(group=self.group)
+                except Exception:
+                    pass
             L.gt_set_compute_stream(None)
+            L.gt_set_apply_stream(None)
             L.gt_storage_destroy(self._h)
+            for p in self._peer_ptrs:
+                L.gt_peer_close(p)
+            if self.transport == "p2p" and collective:
+                try:
+                    self.dist.barrier(group=self.group)  # peers have unmapped before the memory is freed
+                except Exception:
+                    pass
+            for p in self._own_inbox:
+                L.gt_peer_free(p)
+            self._peer_ptrs, self._own_inbox = [], []
             self._h = None
 
     def __del__(self):
         try:
-            self.close()
+            self.close(collective=False)
         except Exception:
             pass

@@ -17,8 +17,9 @@
  *   - one host thread drives one handle at a time (the reference dBG is not thread-safe
  *     either: kmeriterator.hh:64-76 re-bases the graph's own shifter).
  *   - "host" pointers are ordinary CPU memory (pinned memory makes the copies asynchronous);
- *     "_dev" entry points take device pointers already resident in HBM and a CUDA stream
- *     handle (void*, 0 = the library's own stream) and do not synchronise.
+ *     "_dev" entry points take device pointers already resident in HBM.  The library runs on
+ *     its own non-blocking streams (or the ones given to gt_set_compute_stream): whatever
+ *     produced those buffers must have completed, or be ordered before the call on that stream.
  *   - sequences travel as one concatenated byte buffer `bases` plus `offsets[n_reads+1]`
  *     (read r = bases[offsets[r] .. offsets[r+1])).  Per read the semantics are those of
  *     FastxParser<DNA_SIMPLE> + InserterProcessor (parsing/readers.hh:150-219,
@@ -222,11 +223,70 @@ int gt_storage_attach_exchange(gt_storage* st, int which, void* outbox, void* in
  * orders it after that set's exchange and before the set is bucketed into again). */
 int gt_storage_select_store(gt_storage* st, int which);
 int gt_storage_apply_store(gt_storage* st, int which);
+/* Peer-memory transport (the fused hash + exchange path): instead of bucketing into a local
+ * outbox that a collective then ships, k_bucket stores every run of entries straight into the
+ * inbox of the slice's owner over NVLink (plain 16 B stores to peer memory mapped with CUDA IPC),
+ * so the transfer overlaps the hashing run by run and no bulk all-to-all is left -- only the
+ * per-bucket fill counts travel by collective, which is also the "all producers are done" signal.
+ *   inbox of rank q (one per buffer set) = world regions of R_q entries, region p written by rank p
+ *   (R_q = sum of the capacities of the buckets q holds; bucket b sits at its offset inside R_q).
+ * gt_peer_alloc: zeroed device memory that can be exported; gt_peer_export: 64-byte handle to
+ * send to the peers; gt_peer_open: map a peer's allocation into this process (enables peer access);
+ * gt_peer_close / gt_peer_free undo them. */
+void* gt_peer_alloc(uint64_t bytes);
+int gt_peer_free(void* ptr);
+int gt_peer_export(void* ptr, uint8_t handle[64]);
+void* gt_peer_open(const uint8_t handle[64]);
+int gt_peer_close(void* ptr);
+/* inbox_of_rank[world]: device pointers valid in THIS process (entry `rank` = this rank's own
+ * inbox from gt_peer_alloc, the others from gt_peer_open).  fill_send [n_buckets], fill_recv
+ * [world * n_owned] as for gt_storage_attach_exchange; the caller moves fill_send -> fill_recv
+ * (owner-major) after k_bucket, e.g. with one small all-to-all. */
+int gt_storage_attach_peers(gt_storage* st, int which, void* const* inbox_of_rank, void* fill_send,
+                            void* fill_recv);
+/* Storage::query restricted to the slots this rank holds (routed queries on a sharded storage):
+ * counts[i] = AND / min over the tables' slots of hashes[i] that fall in this rank's ranges, the
+ * neutral element (1, 255, 15) where none does; the AND / min over all ranks' answers (an
+ * all-reduce MIN) is exactly Storage::query (bitstorage.cc:87-100, bytestorage.cc:116-139,
+ * nibblestorage.cc:112-130).  d_hashes / d_counts are device pointers; asynchronous on the
+ * compute stream. */
+int gt_query_hashes_local_dev(gt_storage* st, const void* d_hashes, uint64_t n, void* d_counts);
 /* Run the library's kernels on caller-owned CUDA streams (NULL = the library's own), so that
  * they order with the caller's collectives: the compute stream carries pack / hash / bucket,
  * the apply stream k_apply. */
 int gt_set_compute_stream(void* stream);
 int gt_set_apply_stream(void* stream);
+
+/* ---- FASTX front end: FastxParser<DNA_SIMPLE> + FileProcessor (the parsing-to-device pipeline) ---- */
+/* FastxParser(infile, strict, min_length) (parsing/readers.hh:120-122, readers.cc:15-32): kseq
+ * record grammar (parsing/kseq.h:174-214: FASTA / FASTQ, multi-line records, gz-transparent).  A reader
+ * thread inflates ahead of the parser.  NULL + gt_last_error() if the file cannot be opened. */
+typedef struct gt_fastx gt_fastx;
+gt_fastx* gt_fastx_open(const char* path, int strict, uint32_t min_length);
+void gt_fastx_close(gt_fastx* fx);
+/* FastxParser::next (readers.hh:150-219).  1 = a record (pointers into the parser, valid until the next
+ * call; the sequence is validated and upper-cased as DNA_SIMPLE::validate does); 0 = std::nullopt (the
+ * record held a foreign symbol or was shorter than min_length and was skipped, or the end of the file
+ * was reached -- see gt_fastx_stats); -2 = InvalidRead (sequence and quality lengths differ; parsing can
+ * continue); -3 = GoetiaFileException (stream error); -4 = InvalidCharacterException (strict parsers:
+ * a foreign symbol is an error instead of a skip); -5 = NoMoreReadsAvailable. */
+int gt_fastx_next_record(gt_fastx* fx, const char** name, uint64_t* name_len, const char** seq,
+                         uint64_t* seq_len, const char** qual, uint64_t* qual_len);
+/* The same, batched for the device pipeline: appends the sequences of the next kept records to `bases`
+ * (at most max_bases bytes) and their ends to offsets[1..n] (offsets[0] = 0, at most max_reads records).
+ * Returns n (0 = end of file), or an error code as above. */
+int64_t gt_fastx_next_batch(gt_fastx* fx, char* bases, uint64_t max_bases, uint64_t* offsets,
+                            uint64_t max_reads);
+/* n_parsed(), n_skipped(), is_complete() (readers.hh:205-215). */
+int gt_fastx_stats(const gt_fastx* fx, uint64_t* n_parsed, uint64_t* n_skipped, int* is_complete);
+/* FileProcessor<InserterProcessor<dBG>>::process / advance (processors.hh:112-127, 208-229, 304-331):
+ * streams up to max_reads records (0 = the rest of the file) from the parser into the graph --
+ * batch n+1 is parsed into pinned memory while batch n is copied, packed, hashed and inserted.
+ * Returns the k-mers consumed (the processor's "time"); *n_seqs = records processed (records shorter
+ * than K count and contribute 0 k-mers, as InserterProcessor::process_sequence swallows the
+ * SequenceLengthException). */
+int64_t gt_insert_fastx(gt_storage* st, int shifter, int K, gt_fastx* fx, int mode, uint64_t max_reads,
+                        uint64_t* n_seqs);
 
 /* ---- SourmashSketch (sketches/sourmash_sketch.hh:24-82) -------------------------------- */
 /* Sketch(n, K, is_protein=false, dayhoff=false, hp=false, seed, scaled):

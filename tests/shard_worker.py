@@ -61,7 +61,9 @@ def main():
     r0, r1 = min(n_reads, rank * per), min(n_reads, (rank + 1) * per)
     my_b = bases[int(offsets[r0]):int(offsets[r1])]
     my_o = offsets[r0:r1 + 1] - offsets[r0]
-    budget = max(1024, per * 100)  # gt_insert_sequences_dev bounds a batch by its bases
+    # gt_insert_sequences_dev bounds a batch by its bases; x3 because these reads are heavily duplicated
+    # (a 4 kb genome), so bucket loads are far from the uniform share the capacities are sized for
+    budget = max(1024, per * 100 * 3)
     slice_log2 = int(os.environ.get("SHARD_SLICE_LOG2", "10"))
 
     if mode == "cpu":
@@ -105,7 +107,8 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
         gb.init(local)
-        st = ShardedStorage(kind, sizes, budget, slice_log2_bytes=slice_log2)
+        st = ShardedStorage(kind, sizes, budget, slice_log2_bytes=slice_log2,
+                            transport=os.environ.get("SHARD_TRANSPORT", "p2p"))
         plan = st.plan
         d_b = torch.from_numpy(my_b.copy()).cuda()
         d_o = torch.from_numpy(my_o.astype(np.int64)).cuda()
@@ -119,6 +122,22 @@ def main():
         info = st.pending_info()
         assert info["pending_kmers"] == 0
         parts = st.local_tables()
+        # routed queries: every rank asks about its own reads (plus one absent k-mer) and gets the oracle's counts
+        q_o = my_o[:min(my_o.size, 41)]
+        q_b = my_b[:int(q_o[-1])]
+        x_b, x_o = genome_reads(5 + rank, 100, 4000, seed=900 + rank)  # mostly absent k-mers; a different count per rank
+        q_b = np.concatenate([q_b, x_b])
+        q_o = np.concatenate([q_o, x_o[1:] + q_o[-1]])
+        got_q = st.query_sequences(_capi.SHIFTER_CAN, K, q_b, q_o)
+        ref_q = Port(kind, 1, K, sizes)
+        for _ in range(rounds):
+            ref_q.insert_reads(bases, offsets)
+        want_q = ref_q.query_reads(q_b, q_o)
+        if not np.array_equal(got_q, want_q):
+            print("rank %d: routed query differs (%d of %d)" % (rank, int((got_q != want_q).sum()), want_q.size))
+            parts = [p[:0] for p in parts]  # forces a mismatch on rank 0
+        ref_q.close()
+        st.close()
 
     # gather the parts on rank 0 and compare with the oracle
     ok = True

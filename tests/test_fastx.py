@@ -1,0 +1,131 @@
+"""FASTX front end (gt_fastx_*, goetia_b200/parsing.py) against the reference parser.
+
+CPU tests: the parser is host code inside libgoetia_b200.so and needs no GPU.  Expected values come from
+tests/golden/fastx_golden.json and tests/golden/golden.json, both produced by the UNMODIFIED reference
+(FastxParser<DNA_SIMPLE>, parsing/readers.hh:150-219) -- see tests/golden/make_fastx_golden.py.
+The GPU test streams a file through gt_insert_fastx (FileProcessor + InserterProcessor) and compares the
+tables with the oracle's after the same records.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle.binding import Port
+from tests.fastx_cases import cases, write_case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "fastx_golden.json")))
+
+
+def parse_all(fn, strict, min_length, max_bases=1 << 16, max_reads=None, by_record=False):
+    from goetia_b200.parsing import FastxParser
+    p = FastxParser(fn, strict, min_length)
+    seqs = []
+    if by_record:
+        while not p.is_complete():
+            r = p.next()
+            if r is not None:
+                seqs.append(r.sequence.encode())
+    else:
+        while True:
+            b, o = p.next_batch(max_bases, max_reads)
+            if o.size == 1:
+                break
+            seqs.extend(b[int(o[i]):int(o[i + 1])].tobytes() for i in range(o.size - 1))
+    stats = (p.n_parsed(), p.n_skipped(), p.is_complete())
+    p.close()
+    return seqs, stats
+
+
+def check(seqs, stats, want):
+    lens = np.array([len(s) for s in seqs], dtype=np.uint64)
+    assert len(seqs) == want["n_reads"]
+    assert stats[1] == want["n_skipped"]
+    assert stats[2] is True
+    assert int(lens.sum()) == want["n_bases"]
+    assert str(Port.fnv1a(np.frombuffer(b"".join(seqs), dtype=np.uint8))) == want["seq_fnv"]
+    assert str(Port.fnv1a(lens.view(np.uint8))) == want["len_fnv"]
+
+
+@pytest.mark.parametrize("gz", [False, True])
+@pytest.mark.parametrize("case", [c for c in cases()], ids=lambda c: c[0])
+def test_parser_matches_reference(tmp_path, case, gz):
+    from goetia_b200 import parsing
+    name, data, min_length, strict = case
+    fn = write_case(str(tmp_path), name, data, gz)
+    want = GOLD[os.path.basename(fn)]
+    if "error" in want:
+        exc = parsing.InvalidCharacterException if strict else parsing.InvalidRead
+        with pytest.raises(exc):
+            parse_all(fn, strict, min_length, max_bases=8 << 20)
+        return
+    big = want["n_bases"] > (1 << 16)
+    seqs, stats = parse_all(fn, strict, min_length, max_bases=(8 << 20) if big else (1 << 16))
+    check(seqs, stats, want)
+    if not big:
+        # tiny batches (records carried over between calls) and the record-at-a-time API give the same stream
+        longest = max([len(s) for s in seqs] + [1])
+        seqs2, stats2 = parse_all(fn, strict, min_length, max_bases=longest, max_reads=3)
+        assert seqs2 == seqs and stats2 == stats
+        seqs3, stats3 = parse_all(fn, strict, min_length, by_record=True)
+        assert seqs3 == seqs and stats3 == stats
+
+
+def test_records_and_errors(tmp_path, golden):
+    from goetia_b200 import parsing
+    for key in ("_mixed.fa", "_mixed.fq"):
+        g = golden["parser"][key]
+        fn = os.path.join(str(tmp_path), key)
+        with open(fn, "w") as f:
+            f.write(g["text"])
+        p = parsing.FastxParser.build(fn)
+        recs = list(p)
+        assert [r.sequence for r in recs] == g["reads"]
+        assert p.n_skipped() == g["n_skipped"]
+        if key.endswith(".fq"):
+            assert recs[0].name == "q1" and recs[0].quality == "IIIIII"
+        else:
+            assert recs[0].name == "r1" and recs[0].quality == ""
+        with pytest.raises(parsing.NoMoreReadsAvailable):  # readers.hh:151-153
+            p.next()
+    with pytest.raises(parsing.GoetiaFileException):
+        parsing.FastxParser(os.path.join(str(tmp_path), "does-not-exist.fa"))
+    # a truncated quality string raises InvalidRead and counts as skipped; the parser stays usable (readers.hh:198-201)
+    fn = os.path.join(str(tmp_path), "t.fq")
+    with open(fn, "w") as f:
+        f.write("@a\nACGT\n+\nIIIIII\n@b\nGGCC\n+\nIIII\n")
+    p = parsing.FastxParser(fn)
+    with pytest.raises(parsing.InvalidRead):
+        p.next()
+    assert p.n_skipped() == 1
+    assert p.next().sequence == "GGCC"
+
+
+@pytest.mark.gpu
+def test_insert_fastx_matches_oracle(tmp_path, gb):
+    """FileProcessor<InserterProcessor<dBG>>::process over a gz FASTQ == the oracle fed the parser's records."""
+    from goetia_b200.parsing import FastxParser
+    from tests.util import make_graph
+    name, data, min_length, strict = [c for c in cases() if c[0] == "big.fq"][0]
+    fn = write_case(str(tmp_path), name, data, gz=True)
+    K, sizes = 31, gb.get_n_primes_near_x(4, 5_000_000)
+    for kind in (0, 1, 2):
+        g = make_graph(gb, kind, 1, K, sizes)
+        os.environ["GT_FASTX_BATCH_BASES"] = str(1 << 20)  # several batches: the parse-ahead thread is exercised
+        try:
+            n_seqs, n_kmers = g.process_fastx(fn)
+        finally:
+            os.environ.pop("GT_FASTX_BATCH_BASES", None)
+        seqs, _ = parse_all(fn, strict, min_length, max_bases=8 << 20)
+        assert n_seqs == len(seqs) == GOLD["big.fq.gz"]["n_reads"]
+        ref = Port(kind, 1, K, sizes)
+        bases = np.frombuffer(b"".join(seqs), dtype=np.uint8)
+        offsets = np.zeros(len(seqs) + 1, dtype=np.uint64)
+        offsets[1:] = np.cumsum([len(s) for s in seqs])
+        nk_ref, _ = ref.insert_reads(bases, offsets)
+        assert n_kmers == nk_ref
+        for a, b in zip(g.get_raw(), ref.tables()):
+            assert np.array_equal(a, b)
+        ref.close()

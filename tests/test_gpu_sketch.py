@@ -147,6 +147,7 @@ def test_full_size_properties(gb):
     lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device="cuda")
     d_b = lut[codes]
     d_o = (torch.arange(n_reads + 1, dtype=torch.int64, device="cuda") * L)
+    torch.cuda.synchronize()  # the library runs on its own streams: inputs must be complete before the call
     g = _sk(gb, 0, K, 1000)
     nk = g.insert_sequences_dev(d_b.data_ptr(), d_o.data_ptr(), n_reads, n_reads * L)
     assert nk == n_reads * (L - K + 1)
@@ -161,6 +162,7 @@ def test_full_size_properties(gb):
     a, b = _sk(gb, 0, K, 1000), _sk(gb, 0, K, 1000)
     a.insert_sequences_dev(d_b.data_ptr(), one.data_ptr(), 1, n_reads * L)
     rc = lut[(3 - codes).flip(0)]
+    torch.cuda.synchronize()
     b.insert_sequences_dev(rc.data_ptr(), one.data_ptr(), 1, n_reads * L)
     assert np.array_equal(a.mins(), b.mins())
     # spot-check membership of a prefix against the oracle

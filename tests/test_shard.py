@@ -84,13 +84,15 @@ def test_exchange_layout_gloo(kind, world):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("transport", ["p2p", "nccl"])
 @pytest.mark.parametrize("kind", [0, 1, 2])
-def test_sharded_insert_nccl(kind):
+def test_sharded_insert_nccl(kind, transport):
     import torch
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 2 if n < 4 else 4
-    rcs, outs = launch("cuda", kind, world, {"SHARD_TABLE_X": "40000000", "SHARD_READS": "40000", "SHARD_SLICE_LOG2": "16"})
+    rcs, outs = launch("cuda", kind, world, {"SHARD_TABLE_X": "40000000", "SHARD_READS": "40000", "SHARD_SLICE_LOG2": "16",
+                                             "SHARD_ROUNDS": "3", "SHARD_TRANSPORT": transport})
     assert rcs == [0] * world, "\n".join(outs)
     assert "tables bit-exact" in outs[0]
