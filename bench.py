@@ -233,16 +233,25 @@ def main():
     storage = [gb.BitStorage, gb.ByteStorage, gb.NibbleStorage][kind](sizes)
     graph = gb.dBG[type(storage), gb.CanLemireShifter].build(storage, K)
 
+    d_total = torch.zeros(1, dtype=torch.int64, device=dev)  # k-mers consumed, accumulated on the device
+    torch.cuda.synchronize()
+
     def step_resident():
-        nk = 0
+        # nothing in here waits for the GPU until the flush at the end of the step
         for b, n in subs:
-            nk += graph.insert_sequences_dev(b.data_ptr(), offs.data_ptr(), n, n * read_len, mode=gb.MODE_BLIND)
+            graph.insert_sequences_dev_async(b.data_ptr(), offs.data_ptr(), n, n * read_len, mode=gb.MODE_BLIND,
+                                             d_kmer_total_ptr=d_total.data_ptr())
         storage.flush()
-        return nk
+
+    def step_checked():
+        d_total.zero_()
+        torch.cuda.synchronize()
+        step_resident()
+        return int(d_total.item())
 
     kmers_per_step = total_reads * kpr
     for _ in range(args.warmup):
-        assert step_resident() == kmers_per_step
+        assert step_checked() == kmers_per_step
     L.gt_synchronize()
     _capi.check(L.gt_profile_enable(1), "gt_profile_enable")
     sampler = ClockSampler(local_rank)
@@ -400,7 +409,7 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
     max_rank_reads = total_reads // world + (1 if total_reads % world else 0)
     # rounds are smaller than the single-GPU sub-batches: k_apply of round i overlaps k_bucket of round i+1,
     # so only the last round's apply is exposed
-    round_bases = int(os.environ.get("GT_BENCH_ROUND_BASES", 300_000_000))
+    round_bases = int(os.environ.get("GT_BENCH_ROUND_BASES", SUB_BATCH_BASES))
     rounds = max(2, -(-max_rank_reads * read_len // round_bases))
     per_round = -(-max_rank_reads // rounds)
     st = ShardedStorage(kind, sizes, per_round * read_len)
@@ -412,17 +421,24 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
     offs = torch.arange(per_round + 1, dtype=torch.int64, device=dev) * read_len
     torch.cuda.synchronize()
 
+    d_total = torch.zeros(1, dtype=torch.int64, device=dev)  # k-mers consumed, accumulated on the device
+    torch.cuda.synchronize()
+
     def step():
-        nk = 0
+        # no host wait anywhere in a step: rounds are queued back to back on the two streams
         for b, n in subs:
             if n:
-                nk += st.bucket_sequences_dev(_capi.SHIFTER_CAN, K, b.data_ptr(), offs.data_ptr(), n, n * read_len)
+                st.bucket_sequences_dev_async(_capi.SHIFTER_CAN, K, b.data_ptr(), offs.data_ptr(), n, n * read_len,
+                                              d_total.data_ptr())
             st.exchange_and_apply()
-        return nk
 
     kmers_rank = reads_rank * kpr
     for _ in range(args.warmup):
-        assert step() == kmers_rank
+        d_total.zero_()
+        torch.cuda.synchronize()
+        step()
+        st.synchronize()
+        assert int(d_total.item()) == kmers_rank
     st.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
@@ -463,21 +479,35 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
         host_offs = torch.empty(per_round + 1, dtype=torch.int64, pin_memory=True)
         host_offs.copy_(offs)
         dbuf = [torch.empty(per_round * read_len, dtype=torch.uint8, device=dev) for _ in range(2)]
-        doff = torch.empty(per_round + 1, dtype=torch.int64, device=dev)
+        doff = [torch.empty(per_round + 1, dtype=torch.int64, device=dev) for _ in range(2)]
+        copy_stream = torch.cuda.Stream()
         torch.cuda.synchronize()
 
         def step_host():
-            nk = 0
+            # H2D of round i+1 (copy stream) overlaps pack/hash/bucket of round i (compute stream) and k_apply of
+            # round i-1 (apply stream); one result read-back (the k-mer count) at the end of the step
+            consumed = [None, None]
+            with torch.cuda.stream(st.stream):
+                d_total.zero_()
             for i, (h, (b, n)) in enumerate(zip(hosts, subs)):
-                with torch.cuda.stream(st.stream):
-                    d = dbuf[i & 1]
+                d, do = dbuf[i & 1], doff[i & 1]
+                with torch.cuda.stream(copy_stream):
+                    if consumed[i & 1] is not None:
+                        copy_stream.wait_event(consumed[i & 1])
                     d[:h.numel()].copy_(h, non_blocking=True)
-                    doff.copy_(host_offs, non_blocking=True)
+                    do.copy_(host_offs, non_blocking=True)
+                    ready = torch.cuda.Event()
+                    ready.record(copy_stream)
+                st.stream.wait_event(ready)
                 if n:
-                    nk += st.bucket_sequences_dev(_capi.SHIFTER_CAN, K, d.data_ptr(), doff.data_ptr(), n, n * read_len)
+                    st.bucket_sequences_dev_async(_capi.SHIFTER_CAN, K, d.data_ptr(), do.data_ptr(), n, n * read_len,
+                                                  d_total.data_ptr())
+                free = torch.cuda.Event()
+                free.record(st.stream)
+                consumed[i & 1] = free
                 st.exchange_and_apply()
             st.synchronize()
-            return nk
+            return int(d_total.item())  # the step's result read back from the device
 
         for _ in range(min(args.warmup, 2)):
             step_host()

@@ -901,9 +901,31 @@ extern "C" int64_t gt_insert_sequences(gt_storage* st, int shifter, int K, const
     return (int64_t)g_ctx.h_scratch[3];
 }
 
-// Same walk, reads already in HBM as ASCII (d_bases) with device offsets starting at 0.
+// Same walk, reads already in HBM as ASCII (d_bases) with device offsets starting at 0.  d_total (device,
+// may be NULL): the k-mers consumed are ADDED to it on the stream.  Nothing here waits for the GPU.
+static int insert_sequences_dev_queue(gt_storage* st, int shifter, int K, const void* d_bases, const void* d_offsets,
+                                      uint64_t n_reads, uint64_t n_bases, int mode, unsigned long long* d_total);
+
+extern "C" int gt_insert_sequences_dev_async(gt_storage* st, int shifter, int K, const void* d_bases, const void* d_offsets,
+                                             uint64_t n_reads, uint64_t n_bases, int mode, void* d_kmer_total) {
+    return insert_sequences_dev_queue(st, shifter, K, d_bases, d_offsets, n_reads, n_bases, mode,
+                                      static_cast<unsigned long long*>(d_kmer_total));
+}
+
 extern "C" int64_t gt_insert_sequences_dev(gt_storage* st, int shifter, int K, const void* d_bases, const void* d_offsets,
                                             uint64_t n_reads, uint64_t n_bases, int mode) {
+    if (ensure_ctx()) return -1;
+    if (n_reads == 0) return 0;
+    unsigned long long* d_tot = g_ctx.d_scratch + 3;
+    CU(cudaMemsetAsync(d_tot, 0, sizeof(unsigned long long), g_ctx.main));
+    if (insert_sequences_dev_queue(st, shifter, K, d_bases, d_offsets, n_reads, n_bases, mode, d_tot)) return -1;
+    CU(cudaMemcpyAsync(g_ctx.h_scratch + 3, d_tot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, g_ctx.main));
+    CU(cudaStreamSynchronize(g_ctx.main));
+    return (int64_t)g_ctx.h_scratch[3];
+}
+
+static int insert_sequences_dev_queue(gt_storage* st, int shifter, int K, const void* d_bases, const void* d_offsets,
+                                      uint64_t n_reads, uint64_t n_bases, int mode, unsigned long long* d_tot) {
     if (ensure_ctx()) return -1;
     if (!st) return fail("gt_insert_sequences_dev: NULL storage");
     if (K < 1 || K > 65535) return fail("gt_insert_sequences_dev: K=%d out of range (1..65535)", K);
@@ -939,19 +961,17 @@ extern "C" int64_t gt_insert_sequences_dev(gt_storage* st, int shifter, int K, c
     view.d_offsets = const_cast<uint64_t*>(offs);
     view.d_flags = sl.flags.as<uint8_t>();
     view.d_coarse = sl.coarse.as<uint32_t>();
-    unsigned long long* d_tot = g_ctx.d_scratch + 3;
-    CU(cudaMemsetAsync(d_tot, 0, sizeof(unsigned long long), s));
-    k_kmer_counts<<<grid_for(n_reads, 256, 16), 256, 0, s>>>(offs, n_reads, K, view.d_flags, nullptr, nullptr, d_tot); ++g_launches;
-    CU(cudaGetLastError());
+    if (d_tot) {
+        k_kmer_counts<<<grid_for(n_reads, 256, 16), 256, 0, s>>>(offs, n_reads, K, view.d_flags, nullptr, nullptr, d_tot); ++g_launches;
+        CU(cudaGetLastError());
+    }
     // n_bases bounds the k-mers of the batch without a round trip to the host
     if (bucket_usable(st, mode, K, n_bases, n_bases)) {
         if (bucket_insert(st, shifter, view, K, n_bases)) return -1;
     } else if (launch_insert(st, shifter, view, K, mode, nullptr, s)) {
         return -1;
     }
-    CU(cudaMemcpyAsync(g_ctx.h_scratch + 3, d_tot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    return (int64_t)g_ctx.h_scratch[3];
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -158,6 +158,14 @@ class dBG:
                                                                    d_bases_ptr, d_offsets_ptr, n_reads, n_bases,
                                                                    mode), "gt_insert_sequences_dev"))
 
+    def insert_sequences_dev_async(self, d_bases_ptr, d_offsets_ptr, n_reads, n_bases, mode=None, d_kmer_total_ptr=None):
+        """insert_sequences_dev without the host wait: queued on the library's compute stream; the k-mers
+        consumed are added to the device uint64 at d_kmer_total_ptr (optional)."""
+        mode = self.mode if mode is None else mode
+        _capi.check(_capi.lib().gt_insert_sequences_dev_async(self.S.handle, self.hasher.shifter_kind, self.K, d_bases_ptr,
+                                                              d_offsets_ptr, n_reads, n_bases, mode, d_kmer_total_ptr),
+                    "gt_insert_sequences_dev_async")
+
     def flush(self):
         self.S.flush()
 

@@ -161,6 +161,13 @@ int64_t gt_insert_batch(gt_storage* st, int shifter, int K, gt_batch* b, int mod
 int64_t gt_insert_sequences_dev(gt_storage* st, int shifter, int K, const void* d_bases,
                                 const void* d_offsets, uint64_t n_reads, uint64_t n_bases, int mode);
 
+/* The same without any host wait: everything is queued on the compute stream and the call returns at
+ * once (0 / <0).  d_kmer_total (device uint64, may be NULL): the k-mers consumed are ADDED to it on
+ * the stream.  The caller keeps d_bases / d_offsets alive until the stream has passed the call. */
+int gt_insert_sequences_dev_async(gt_storage* st, int shifter, int K, const void* d_bases,
+                                  const void* d_offsets, uint64_t n_reads, uint64_t n_bases, int mode,
+                                  void* d_kmer_total);
+
 /* ---- write-combining of blind inserts --------------------------------------------------- */
 /* GT_MODE_BLIND inserts into tables larger than L2 are not applied one by one: each update
  * is appended to the bucket of its table slice and applied slice by slice (DESIGN.md,
