@@ -80,38 +80,52 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 100 ms while the timed region runs."""
+    """nvidia-smi clocks + throttle reasons sampled every 20 ms; only the samples taken between begin() and
+    stop() -- the timed region -- are reported."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.t0 = index, None, [], None
 
     def start(self):
+        """Launch the sampler and wait (<= 3 s) until it delivers, so that a short timed region is covered."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t_end = time.time() + 3.0
+            while not self.lines and time.time() < t_end:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
+        self.begin()
+
+    def begin(self):
+        self.t0 = time.time()
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
     def stop(self):
         if not self.proc:
             return None
+        t1 = time.time()
+        time.sleep(0.03)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        inside = [ln for (t, ln) in self.lines if self.t0 <= t <= t1 + 0.03]
+        if not inside:  # region shorter than one sampling period: the nearest sample
+            inside = [ln for (_, ln) in self.lines[-1:]]
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -440,11 +454,12 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
         st.synchronize()
         assert int(d_total.item()) == kmers_rank
     st.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # before the barrier: its start-up must not skew the ranks
     dist.barrier()
     torch.cuda.synchronize()
     _capi.check(L.gt_profile_enable(1), "gt_profile_enable")
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.begin()
     launches0 = L.gt_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(st.stream)

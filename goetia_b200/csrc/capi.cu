@@ -1462,6 +1462,71 @@ extern "C" int64_t gt_median_count_at_least(gt_storage* st, int shifter, int K, 
     return (int64_t)g_ctx.h_scratch[3];
 }
 
+// DiginormFilter over a batch, batch-synchronous: every read of the CALL is judged
+// against the table state at the start of the call (median_count_at_least, diginorm.hh:35-68), then the kept
+// reads are inserted (filter_sequence, :111-119).  A call of one read reproduces the reference's serial filter
+// exactly.  Returns the k-mers of all judged reads (the processor's "time": filter_sequence returns len-K+1
+// whether or not the read passes); keep[r] = 1 for reads that passed (they are the ones FilterProcessor writes
+// out, processors.hh:389-417); *n_kept = how many.
+extern "C" int64_t gt_diginorm_sequences(gt_storage* st, int shifter, int K, const char* bases, const uint64_t* offsets,
+                                          uint64_t n_reads, uint32_t cutoff, uint8_t* keep, uint64_t* n_kept) {
+    if (check_reads("gt_diginorm_sequences", bases, offsets, n_reads, K)) return -1;
+    if (!st || !keep) return fail("gt_diginorm_sequences: NULL argument");
+    if (st->world > 1) return fail("gt_diginorm_sequences: not available on a sharded storage");
+    if (pending_flush_sync(st)) return -1;
+    if (validate_offsets("gt_diginorm_sequences", offsets, n_reads)) return -1;
+    if (n_kept) *n_kept = 0;
+    if (n_reads == 0) return 0;
+    CU(cudaSetDevice(g_ctx.device));
+    std::vector<uint64_t> cuts;
+    chunk_ranges(offsets, n_reads, cuts);
+    const size_t n_chunks = cuts.size() - 1;
+    unsigned long long* d_tot = g_ctx.d_scratch + 3;   // k-mers judged
+    unsigned long long* d_kept = g_ctx.d_scratch + 5;  // reads kept
+    CU(cudaMemsetAsync(d_tot, 0, sizeof(unsigned long long), g_ctx.slot[0].stream));
+    CU(cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long), g_ctx.slot[0].stream));
+    CU(cudaStreamSynchronize(g_ctx.slot[0].stream));
+    // pass 0 judges every chunk; pass 1 stages the chunks again and inserts the kept reads.  With a single
+    // chunk (the usual batch) the judged chunk is still resident and is inserted straight away.
+    for (int pass = 0; pass < 2; ++pass) {
+        for (size_t c = 0; c < n_chunks; ++c) {
+            Slot& sl = g_ctx.slot[c & 1];
+            cudaStream_t s = sl.stream;
+            const uint64_t r0 = cuts[c], r1 = cuts[c + 1], nr = r1 - r0;
+            gt_batch view;
+            if (stage_chunk(sl, bases, offsets, r0, r1, view)) return -1;
+            if (sl.kcount.reserve(nr * 8, s) || sl.hits.reserve(nr * 4, s) || sl.out8.reserve(nr, s)) return -1;
+            uint8_t* d_keep = sl.out8.as<uint8_t>();
+            if (pass == 0) {
+                k_kmer_counts<<<grid_for(nr, 256, 16), 256, 0, s>>>(view.d_offsets, nr, K, view.d_flags, sl.kcount.as<uint64_t>(), nullptr, d_tot); ++g_launches;
+                CU(cudaGetLastError());
+                CU(cudaMemsetAsync(sl.hits.p, 0, nr * 4, s));
+                WalkArgs a = make_args(view, K);
+                a.hits = sl.hits.as<uint32_t>();
+                a.cutoff = cutoff;
+                if (launch_walk_kind<OP_MEDIAN, false>(shifter, a, st->ts, s)) return -1;
+                k_diginorm_keep<<<grid_for(nr, 256, 16), 256, 0, s>>>(sl.kcount.as<uint64_t>(), a.hits, nr, view.d_flags, d_keep, d_kept); ++g_launches;
+                CU(cudaGetLastError());
+                CU(cudaMemcpyAsync(keep + r0, d_keep, nr, cudaMemcpyDeviceToHost, s));
+                if (n_chunks > 1) continue;
+            } else {
+                // the judgement of pass 0 (host `keep`) comes back as flags
+                CU(cudaMemcpyAsync(d_keep, keep + r0, nr, cudaMemcpyHostToDevice, s));
+                k_flag_unkept<<<grid_for(nr, 256, 16), 256, 0, s>>>(d_keep, nr, view.d_flags); ++g_launches;
+                CU(cudaGetLastError());
+            }
+            if (launch_insert(st, shifter, view, K, GT_MODE_BLIND, nullptr, s)) return -1;
+        }
+        CU(cudaStreamSynchronize(g_ctx.slot[0].stream));
+        CU(cudaStreamSynchronize(g_ctx.slot[1].stream));
+        if (n_chunks == 1) break;
+    }
+    CU(cudaMemcpy(g_ctx.h_scratch + 3, d_tot, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(g_ctx.h_scratch + 5, d_kept, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (n_kept) *n_kept = g_ctx.h_scratch[5];
+    return (int64_t)g_ctx.h_scratch[3];
+}
+
 // ------------------------------------------------------------------------------------------
 // hash-vector members
 // ------------------------------------------------------------------------------------------

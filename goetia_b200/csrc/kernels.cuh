@@ -612,6 +612,31 @@ __global__ void __launch_bounds__(256) k_median_decide(const uint64_t* __restric
     }
 }
 
+// DiginormFilter::Filter::filter_sequence (diginorm.hh:111-119), the keep decision of a batch: a read is kept
+// (and then inserted) iff it is walkable and median_count_at_least is false.  Reads that are not kept get the
+// READ_INVALID flag so that the insert walk that follows skips them.
+__global__ void __launch_bounds__(256) k_diginorm_keep(const uint64_t* __restrict__ kcount, const uint32_t* __restrict__ hits,
+                                                        uint64_t n_reads, uint8_t* __restrict__ flags, uint8_t* __restrict__ keep,
+                                                        unsigned long long* __restrict__ n_kept) {
+    unsigned long long mine = 0;
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n_reads;
+         r += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t n = kcount[r];
+        const unsigned min_req = (unsigned)(0.5 + (double)((float)n / 2.0f));
+        const bool k = n > 0 && hits[r] < min_req;
+        keep[r] = k ? 1 : 0;
+        if (!k) flags[r] |= READ_INVALID;
+        mine += k;
+    }
+    for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_kept, mine);
+}
+
+__global__ void __launch_bounds__(256) k_flag_unkept(const uint8_t* __restrict__ keep, uint64_t n_reads, uint8_t* __restrict__ flags) {
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n_reads; r += (uint64_t)gridDim.x * blockDim.x)
+        if (!keep[r]) flags[r] |= READ_INVALID;
+}
+
 // ------------------------------------------------------------------------------------------
 // Hash-vector entry points (Storage::insert / query on raw hash values; the shape of the
 // reference's own storage micro-benchmark, src/goetia/benchmarks/bench_storage.cc:17-61).

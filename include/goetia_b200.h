@@ -138,6 +138,15 @@ int64_t gt_median_count_at_least(gt_storage* st, int shifter, int K, const char*
                                  const uint64_t* offsets, uint64_t n_reads, uint32_t cutoff,
                                  uint8_t* pass, uint8_t* status);
 
+/* DiginormFilter::Filter::filter_sequence over a batch (diginorm.hh:111-119; FilterProcessor,
+ * processors.hh:389-417), batch-synchronous: every read of the call is judged against the table state
+ * at the start of the call, then the reads that passed (median count below cutoff) are inserted.  A call
+ * of one read is the reference's serial filter.  keep[r] = 1 for passing reads, *n_kept = their number;
+ * returns the k-mers of all judged reads (filter_sequence's second tuple member, summed). */
+int64_t gt_diginorm_sequences(gt_storage* st, int shifter, int K, const char* bases,
+                              const uint64_t* offsets, uint64_t n_reads, uint32_t cutoff, uint8_t* keep,
+                              uint64_t* n_kept);
+
 /* ---- device-resident batches (the parsing-to-device pipeline's product) --------------- */
 /* Upload + validate + 2-bit pack a batch (A=0 C=1 G=2 T=3; flat base p at bits 2*(p%32) of
  * 64-bit word p/32).  The batch stays in HBM until destroyed and can be inserted / queried
