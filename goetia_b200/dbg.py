@@ -235,6 +235,38 @@ class dBG:
             raise InvalidCharacterException("sequence holds a non-ACGT character")
         return (tot, int(n_new[0])) if want_n_new else tot
 
+    def _hashes_and_values(self, sequence):
+        hs = self.hasher.hashes(sequence if isinstance(sequence, str) else sequence.decode("ascii"))
+        return hs, np.array([h.value() for h in hs], dtype=np.uint64)
+
+    def insert_sequence_hashes(self, sequence):
+        """insert_sequence(sequence, std::vector<hash_type>& hashes), dbg.hh:282-294 -> (len-K+1, hashes)."""
+        hs, vals = self._hashes_and_values(sequence)
+        self.S.insert_many(vals, mode=MODE_EXACT, want_new=False)
+        return len(hs), hs
+
+    def insert_sequence_new_kmers(self, sequence):
+        """insert_sequence(sequence, std::set<hash_type>& new_kmers), dbg.hh:267-280 -> (len-K+1, set of the
+        hashes whose insert() returned true).  GT_MODE_EXACT gives the reference's serial first-toucher rule."""
+        hs, vals = self._hashes_and_values(sequence)
+        is_new = self.S.insert_many(vals, mode=MODE_EXACT)
+        return len(hs), {h for h, nw in zip(hs, is_new) if nw}
+
+    def insert_sequence_counts(self, sequence):
+        """insert_sequence(sequence, hashes, counts), dbg.hh:249-265: counts[j] = insert_and_query(k-mer j),
+        each k-mer seeing the earlier ones of the same sequence -> (len-K+1, hashes, counts)."""
+        hs, _ = self._hashes_and_values(sequence)
+        return len(hs), hs, [self.S.insert_and_query(h.value()) for h in hs]
+
+    def query_sequence_hashes(self, sequence, want_new=False):
+        """query_sequence(sequence, counts, hashes[, new_hashes]), dbg.hh:364-394: new_hashes = the hashes whose
+        count is 0."""
+        hs, vals = self._hashes_and_values(sequence)
+        counts = [int(c) for c in self.S.query_many(vals)]
+        if want_new:
+            return counts, hs, {h for h, c in zip(hs, counts) if c == 0}
+        return counts, hs
+
     def query_sequence(self, sequence):
         bases, offsets = self._one(sequence)
         counts, status = self.query_sequences(bases, offsets, want_status=True)

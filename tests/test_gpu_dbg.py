@@ -235,3 +235,45 @@ def test_update_from_and_resident_batch(gb):
     ref3 = Port(0, 1, K, sizes)
     ref3.insert_reads(b1, o1)
     assert_tables_equal(g3.get_raw(), ref3.tables())
+
+
+@pytest.mark.parametrize("kind,_n", STORAGES)
+def test_sequence_overloads(gb, kind, _n):
+    """The other insert_sequence / query_sequence overloads of dbg.hh:249-294, 364-394, replayed k-mer by k-mer
+    on the oracle (insert / insert_and_query / query on hash values)."""
+    K = 21
+    sizes = gb.get_n_primes_near_x(4, 50_021)  # small tables: collisions and repeated k-mers do occur
+    g = make_graph(gb, kind, 1, K, sizes)
+    ref = Port(kind, 1, K, sizes)
+    bases, offsets = genome_reads(12, 90, 300, seed=21)  # overlapping reads: many k-mers repeat
+    for r in range(12):
+        s = read_str(bases, offsets, r)
+        fw, rc = Port.hash_sequence(1, K, s)
+        vals = np.minimum(fw, rc)
+        if r % 3 == 0:
+            n, hs, counts = g.insert_sequence_counts(s)
+            assert counts == [int(ref.insert_and_query(int(v))) for v in vals]
+        elif r % 3 == 1:
+            n, new = g.insert_sequence_new_kmers(s)
+            want_new = {int(v) for v in vals if ref.insert(int(v))}
+            assert {h.value() for h in new} == want_new
+            hs = None
+        else:
+            n, hs = g.insert_sequence_hashes(s)
+            for v in vals:
+                ref.insert(int(v))
+        assert n == len(s) - K + 1
+        if hs is not None:
+            assert [h.value() for h in hs] == [int(v) for v in vals]
+            assert [(h.fw_hash, h.rc_hash) for h in hs] == [(int(a), int(b)) for a, b in zip(fw, rc)]
+    for a, b in zip(g.get_raw(), ref.tables()):
+        assert np.array_equal(a, b)
+    assert g.n_unique() == ref.stats()[0] and g.n_occupied() == ref.stats()[1]
+    q_b, q_o = genome_reads(3, 90, 300, seed=22)
+    for r in range(3):
+        s = read_str(q_b, q_o, r)
+        counts, hs, new = g.query_sequence_hashes(s, want_new=True)
+        want = ref.query_sequence(s).tolist()
+        assert counts == want
+        assert {h.value() for h in new} == {h.value() for h, c in zip(hs, want) if c == 0}
+    ref.close()
