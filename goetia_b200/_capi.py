@@ -39,6 +39,7 @@ SIGNATURES = {
     "gt_storage_upload_table": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "gt_storage_stats": (C.c_int, [C.c_void_p, u64p, u64p]),
     "gt_storage_set_n_unique": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "gt_storage_checksum": (C.c_int, [C.c_void_p, C.c_int, u64p]),
     "gt_storage_update_from": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gt_storage_device_table": (C.c_void_p, [C.c_void_p, C.c_int]),
     "gt_insert_hashes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),
@@ -78,6 +79,7 @@ SIGNATURES = {
     "gt_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gt_peer_open": (C.c_void_p, [C.c_void_p]),
     "gt_peer_close": (C.c_int, [C.c_void_p]),
+    "gt_storage_inbox_bytes": (C.c_uint64, [C.c_void_p, C.c_int]),
     "gt_storage_attach_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gt_query_hashes_local_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "gt_storage_select_store": (C.c_int, [C.c_void_p, C.c_int]),

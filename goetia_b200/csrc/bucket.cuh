@@ -55,8 +55,36 @@ struct ProducePlan {
     const uint32_t* bcap;             // [n_buckets] capacity in entries (multiple of 4)
     uint32_t* bfill;                  // [n_buckets] cursor; can exceed bcap (excess handled at once)
     unsigned long long* n_direct;     // updates that overflowed a bucket and were applied directly
-    unsigned long long* n_dropped;    // overflowed updates of slots this rank does not hold (an error)
+    unsigned long long* n_dropped;    // overflowed updates of foreign slots that found the overflow list full too (an error)
+    // Sharded storages, peer transport: an update that overflows the bucket of a slice held by rank q is
+    // posted as a full (table, slot) record to this rank's overflow list in q's inbox (rare path).
+    // Counting storages: an update that overflows the bucket of a slice held HERE is not applied by k_bucket
+    // itself (a saturating CAS must not run beside the optimistic k_apply_add of the other store, see K2 for
+    // the counting storages); it is parked in the store's spill list and applied after that store's buckets.
+    unsigned long long* own_spill;    // [own_spill_cap] (table, slot) records; NULL for BitStorage
+    uint32_t* own_spill_fill;
+    uint32_t own_spill_cap;
+    const uint8_t* bowner;            // [n_buckets] owner rank of each bucket (NULL: no overflow lists)
+    unsigned long long* const* ovf_ptr;  // [world] this rank's list in the inbox of rank q
+    uint32_t* ovf_fill;               // [world] local cursors (travel with the bucket fill counts)
+    uint32_t ovf_cap;                 // records per list
 };
+
+// overflow record: table in the top 5 bits (MAX_TABLES == 32), global slot below (table sizes <= 2^59 here)
+__device__ __forceinline__ unsigned long long ovf_pack(int t, uint64_t bin) { return ((unsigned long long)t << 59) | bin; }
+
+// an update this rank cannot apply itself and cannot bucket: post it to the owner's overflow list
+__device__ __forceinline__ void post_foreign(const ProducePlan& bp, int t, uint32_t b, uint64_t bin, unsigned long long& dropped) {
+    if (bp.bowner) {
+        const int q = bp.bowner[b];
+        const uint32_t k = atomicAdd(bp.ovf_fill + q, 1u);
+        if (k < bp.ovf_cap) {
+            bp.ovf_ptr[q][k] = ovf_pack(t, bin);
+            return;
+        }
+    }
+    ++dropped;
+}
 
 // What k_apply walks: one item per (slice, source rank) in slice order.
 struct ApplyItem {
@@ -100,6 +128,25 @@ constexpr int BK_SUB = 8;  // positions per thread and sub-step
 constexpr int BK_OWN = BK_MAX_BUCKETS / TILE_THREADS;  // buckets a lane may own (4)
 constexpr uint32_t BK_NONE = 0xFFFFFFFFu;
 
+// an update of a slot held here whose bucket is full: BitStorage applies it on the spot (OR commutes with
+// everything); the counting storages park it (see ProducePlan::own_spill)
+template <int KIND>
+__device__ __forceinline__ void apply_own_overflow(const TableSet& ts, const ProducePlan& bp, int t, uint64_t bin,
+                                                   unsigned long long& direct, unsigned long long& dropped) {
+    if constexpr (KIND == 0) {
+        slot_insert<0, false>(ts.ptr[t], bin);
+        ++direct;
+    } else {
+        const uint32_t k = atomicAdd(bp.own_spill_fill, 1u);
+        if (k < bp.own_spill_cap) {
+            bp.own_spill[k] = ovf_pack(t, bin);
+            ++direct;
+        } else {
+            ++dropped;
+        }
+    }
+}
+
 template <int KIND>
 __device__ __forceinline__ void bucket_spill(const TableSet& ts, const ProducePlan& bp, int t, uint32_t b, uint32_t off,
                                              unsigned long long& direct, unsigned long long& dropped) {
@@ -111,10 +158,9 @@ __device__ __forceinline__ void bucket_spill(const TableSet& ts, const ProducePl
     }
     const uint64_t bin = ((uint64_t)(b - bp.first[t]) << bp.shift) + off;
     if (bin >= bp.own_lo[t] && bin < bp.own_hi[t]) {
-        slot_insert<KIND, false>(ts.ptr[t], bin);
-        ++direct;
+        apply_own_overflow<KIND>(ts, bp, t, bin, direct, dropped);
     } else {
-        ++dropped;
+        post_foreign(bp, t, b, bin, dropped);
     }
 }
 
@@ -316,10 +362,9 @@ k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts
                                 if (offs[k] == BK_PAD) continue;
                                 const uint64_t bin = ((uint64_t)(b - bp.first[t]) << bp.shift) + offs[k];
                                 if (bin >= bp.own_lo[t] && bin < bp.own_hi[t]) {
-                                    slot_insert<KIND, false>(ts.ptr[t], bin);
-                                    ++direct;
+                                    apply_own_overflow<KIND>(ts, bp, t, bin, direct, dropped);
                                 } else {
-                                    ++dropped;
+                                    post_foreign(bp, t, b, bin, dropped);
                                 }
                             }
                         }
@@ -353,10 +398,12 @@ k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts
 // ------------------------------------------------------------------------------------------
 // chunk_start[n_buckets+1]: first CTA of each bucket, host-built from the capacities, so the
 // grid needs no device-side planning; CTAs past a bucket's fill exit at once.
+// only_failed != NULL: apply only the slices whose conservation check failed (replay pass of the counting
+// storages, see below); items_per_slice consecutive items belong to one slice.
 template <int KIND>
 __global__ void __launch_bounds__(AP_THREADS)
 k_apply(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ items, const uint32_t* __restrict__ chunk_start,
-        int n_items) {
+        int n_items, const unsigned long long* __restrict__ only_failed = nullptr, int items_per_slice = 1) {
     __shared__ uint32_t s_b;
     if (threadIdx.x == 0) {
         // item of this CTA: largest b with chunk_start[b] <= blockIdx.x
@@ -369,6 +416,7 @@ k_apply(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ items
     }
     __syncthreads();
     const uint32_t b = s_b;
+    if (only_failed && __ldcg(only_failed + b / (uint32_t)items_per_slice) == 0ull) return;
     const ApplyItem it = items[b];
     const uint32_t fill = min(__ldcg(it.fill), it.cap);
     const uint32_t e0 = (blockIdx.x - __ldg(chunk_start + b)) * (uint32_t)AP_CHUNK;
@@ -391,6 +439,138 @@ k_apply(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ items
         for (uint32_t e = threadIdx.x; e < n; e += AP_THREADS) {
             uint32_t x = __ldcs(src + e0 + e);
             if (x != BK_PAD) slot_insert<KIND, false>(tbl, x);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2 for the counting storages (ByteStorage / NibbleStorage).
+//
+// A saturating increment by CAS costs a load plus a compare-and-swap per update and runs at a fraction of the
+// fire-and-forget atomic rate (measured on B200: ~26 G updates/s against ~200 G RED/s; an atomicAdd that
+// returns its old value manages ~55 G/s).  But saturation is rare, and 32-bit word arithmetic is linear: as long
+// as no counter of a slice is hit while it stands at its maximum, a plain RED.ADD of 1 << shift IS the saturating
+// increment.  So a slice is applied optimistically and checked by a conservation law:
+//   k_slice_sums<-1>   delta[slice] -= sum of all counters of the slice          (before)
+//   k_apply_red        every update is one RED.ADD; delta[slice] -= updates applied
+//   k_slice_sums<+1>   delta[slice] += sum of all counters of the slice          (after)
+// An add that lands on a counter below its maximum raises the slice's counter sum by exactly 1; one that lands on
+// a counter AT its maximum wraps it (and carries into the neighbour, or off the word) and changes the sum by
+// <= 1 - max.  Hence delta[slice] == 0 <=> no add wrapped <=> the slice already holds min(max, hits).  For the
+// (rare) slices with delta != 0:
+//   k_apply_red<UNDO>  subtracts every update again -- exact whatever the wraps did to neighbouring counters,
+//                      because add and subtract cancel mod 2^32;
+//   k_apply(only_failed) replays the updates with the saturating CAS.
+// NibbleStorage saturates routinely (that is what 4-bit counters are for), so its default stays the CAS apply;
+// GT_APPLY_CAS=0 / 1 forces the optimistic / the CAS apply for either storage.
+// Nothing else writes the tables meanwhile: k_bucket parks its own overflow (ProducePlan::own_spill) and the direct
+// writers are ordered against the apply stream (direct_begin / direct_end).  Final bytes are bit-exact.
+// Items of one slice are consecutive (items_per_slice = ranks that produced for it): slice = item / items_per_slice.
+// ------------------------------------------------------------------------------------------
+struct SliceDesc {
+    uint64_t slot0, slots;
+    uint32_t table;
+};
+
+template <int KIND>
+__device__ __forceinline__ void counter_addr(uint32_t off, uint32_t& word, uint32_t& sh) {
+    if constexpr (KIND == 1) {
+        word = off >> 2;
+        sh = (off & 3u) * 8u;
+    } else {
+        word = off >> 3;
+        sh = ((off >> 1) & 3u) * 8u + ((off & 1u) ? 0u : 4u);
+    }
+}
+
+// sum of the 4 byte counters / 8 nibble counters of a table word
+template <int KIND>
+__device__ __forceinline__ uint32_t counter_sum(uint32_t x) {
+    if constexpr (KIND == 1) return __dp4a(x, 0x01010101u, 0u);
+    else return __dp4a(x & 0x0f0f0f0fu, 0x01010101u, __dp4a((x >> 4) & 0x0f0f0f0fu, 0x01010101u, 0u));
+}
+
+// grid (x, n_slices): delta[slice] += SIGN * (sum of the counters of the slice)
+template <int KIND, int SIGN>
+__global__ void __launch_bounds__(256) k_slice_sums(const __grid_constant__ TableSet ts, const SliceDesc* __restrict__ slices,
+                                                     unsigned long long* __restrict__ delta) {
+    const SliceDesc sd = slices[blockIdx.y];
+    constexpr uint32_t spw = KIND == 1 ? 4u : 8u;
+    const uint32_t* tbl = ts.ptr[sd.table] + sd.slot0 / spw;  // slices start on a word boundary
+    const uint64_t n_words = (sd.slots + spw - 1) / spw;      // a table's last word may be partial: its padding is zero
+    unsigned long long mine = 0;
+    const uint4* v = reinterpret_cast<const uint4*>(tbl);
+    const uint64_t n4 = (reinterpret_cast<uintptr_t>(tbl) & 15) == 0 ? n_words / 4 : 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 x = __ldcg(v + i);
+        mine += counter_sum<KIND>(x.x) + counter_sum<KIND>(x.y) + counter_sum<KIND>(x.z) + counter_sum<KIND>(x.w);
+    }
+    for (uint64_t w = n4 * 4 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words; w += (uint64_t)gridDim.x * blockDim.x)
+        mine += counter_sum<KIND>(__ldcg(tbl + w));
+    for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(delta + blockIdx.y, SIGN > 0 ? mine : 0ull - mine);
+}
+
+// UNDO = false: the optimistic pass.  UNDO = true: subtract the same updates again, only in the slices whose
+// check failed (delta != 0 after k_slice_sums<+1>); delta is left untouched so that the replay sees it too.
+template <int KIND, bool UNDO>
+__global__ void __launch_bounds__(AP_THREADS)
+k_apply_red(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ items, const uint32_t* __restrict__ chunk_start,
+            int n_items, int items_per_slice, unsigned long long* __restrict__ delta) {
+    static_assert(KIND == 1 || KIND == 2, "counting storages only");
+    __shared__ uint32_t s_b;
+    if (threadIdx.x == 0) {
+        uint32_t lo = 0, hi = (uint32_t)n_items;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(chunk_start + mid) <= blockIdx.x) lo = mid; else hi = mid;
+        }
+        s_b = lo;
+    }
+    __syncthreads();
+    const uint32_t b = s_b;
+    if (UNDO && __ldcg(delta + b / (uint32_t)items_per_slice) == 0ull) return;
+    const ApplyItem it = items[b];
+    const uint32_t fill = min(__ldcg(it.fill), it.cap);
+    const uint32_t e0 = (blockIdx.x - __ldg(chunk_start + b)) * (uint32_t)AP_CHUNK;
+    if (e0 >= fill) return;
+    uint32_t* tbl = ts.ptr[it.table] + (KIND == 1 ? (it.slot0 >> 2) : (it.slot0 >> 3));
+    const uint32_t* src = it.src;
+    const uint32_t n = min((uint32_t)AP_CHUNK, fill - e0);
+    uint32_t applied = 0;
+    auto one = [&](uint32_t off) {
+        if (off == BK_PAD) return;
+        uint32_t word, sh;
+        counter_addr<KIND>(off, word, sh);
+        atomicAdd(tbl + word, UNDO ? 0u - (1u << sh) : (1u << sh));  // result unused: RED.ADD
+        ++applied;
+    };
+    if (n == AP_CHUNK && ((reinterpret_cast<uintptr_t>(src + e0) & 15) == 0)) {
+        const uint4* v = reinterpret_cast<const uint4*>(src + e0);
+#pragma unroll
+        for (int k = 0; k < AP_PER_THREAD / 4; ++k) {
+            const uint4 x = __ldcs(v + k * AP_THREADS + threadIdx.x);
+            one(x.x); one(x.y); one(x.z); one(x.w);
+        }
+    } else {
+        for (uint32_t e = threadIdx.x; e < n; e += AP_THREADS) one(__ldcs(src + e0 + e));
+    }
+    if (!UNDO) {
+        for (int o = 16; o; o >>= 1) applied += __shfl_down_sync(0xffffffffu, applied, o);
+        if ((threadIdx.x & 31) == 0 && applied) atomicAdd(delta + b / (uint32_t)items_per_slice, 0ull - (unsigned long long)applied);
+    }
+}
+
+// Overflow lists received from the peers (rare path): world lists of up to `cap` (table, slot) records.
+template <int KIND>
+__global__ void __launch_bounds__(256) k_apply_overflow(const __grid_constant__ TableSet ts, const unsigned long long* __restrict__ lists,
+                                                         const uint32_t* __restrict__ counts, uint32_t count_stride, uint32_t cap, int world) {
+    for (int q = 0; q < world; ++q) {
+        const uint32_t n = min(__ldcg(counts + (size_t)q * count_stride), cap);
+        const unsigned long long* src = lists + (size_t)q * cap;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const unsigned long long rec = src[i];
+            slot_insert<KIND, false>(ts.ptr[(int)(rec >> 59)], rec & ((1ull << 59) - 1));
         }
     }
 }

@@ -427,6 +427,27 @@ extern "C" int gt_storage_stats(gt_storage* st, uint64_t* n_unique, uint64_t* n_
     return 0;
 }
 
+// Position-weighted checksum of table i (kernels.cuh, k_checksum).  Linear in the table's words and indexed by
+// GLOBAL word position, so the checksums of the parts of a sharded storage add up (mod 2^64) to the checksum of
+// the whole table.
+extern "C" int gt_storage_checksum(gt_storage* st, int i, uint64_t* out) {
+    if (ensure_ctx()) return -1;
+    if (!st || !out || i < 0 || i >= st->n) return fail("gt_storage_checksum: bad argument");
+    if (pending_flush_sync(st)) return -1;
+    CU(cudaDeviceSynchronize());
+    cudaStream_t s = g_ctx.main;
+    unsigned long long* d_sum = g_ctx.d_scratch + 6;
+    CU(cudaMemsetAsync(d_sum, 0, sizeof(unsigned long long), s));
+    const uint64_t n_words = st->alloc_bytes[i] / 4;
+    const uint64_t word0 = st->own_lo[i] / (uint64_t)slots_per_word(st->kind);
+    k_checksum<<<grid_for(n_words, 256 * 8, 8), 256, 0, s>>>(static_cast<const uint32_t*>(st->slab[i]), n_words, word0, d_sum); ++g_launches;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(g_ctx.h_scratch + 6, d_sum, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    *out = g_ctx.h_scratch[6];
+    return 0;
+}
+
 extern "C" int gt_storage_set_n_unique(gt_storage* st, uint64_t n_unique) {
     if (ensure_ctx()) return -1;
     if (!st) return fail("gt_storage_set_n_unique: NULL storage");
@@ -766,8 +787,15 @@ static int exact_map(uint64_t claims, cudaStream_t s, ClaimMap& m) {
     return 0;
 }
 
+static int launch_insert_unordered(gt_storage* st, int shifter, const gt_batch& b, int K, int mode, uint64_t* d_n_new, cudaStream_t s);
+// the direct path: k_walk applies every update to the tables itself
 static int launch_insert(gt_storage* st, int shifter, const gt_batch& b, int K, int mode, uint64_t* d_n_new, cudaStream_t s) {
     if (st->world > 1) return fail("a sharded storage takes GT_MODE_BLIND inserts through its exchange only (attach it first)");
+    if (direct_begin(st, s)) return -1;
+    if (launch_insert_unordered(st, shifter, b, K, mode, d_n_new, s)) return -1;
+    return direct_end(st, s);
+}
+static int launch_insert_unordered(gt_storage* st, int shifter, const gt_batch& b, int K, int mode, uint64_t* d_n_new, cudaStream_t s) {
     WalkArgs a = make_args(b, K);
     a.n_unique = st->d_n_unique;
     a.n_new = d_n_new;
@@ -985,7 +1013,7 @@ extern "C" int gt_shard_plan(int kind, const uint64_t* tablesizes, int n_tables,
     for (int i = 0; i < n_tables; ++i)
         if (tablesizes[i] == 0) return fail("gt_shard_plan: empty table");
     PlanHost P;
-    if (make_plan(kind, tablesizes, n_tables, world, budget_kmers, slice_log2_bytes > 0 ? slice_log2_bytes : 25, P)) return -1;
+    if (make_plan(kind, tablesizes, n_tables, world, budget_kmers, slice_log2_bytes > 0 ? slice_log2_bytes : default_slice_log2_bytes(kind), P)) return -1;
     shift_nb[0] = P.shift;
     shift_nb[1] = P.nb;
     for (int b = 0; b < P.nb; ++b) {
@@ -1009,7 +1037,7 @@ extern "C" gt_storage* gt_storage_create_sharded(int kind, const uint64_t* table
     if (kind < 0 || kind > 2 || !tablesizes || n_tables < 1 || n_tables > MAX_TABLES) { fail("gt_storage_create_sharded: bad argument"); return nullptr; }
     if (budget_kmers == 0 || budget_kmers > (1ull << 31)) { fail("gt_storage_create_sharded: budget_kmers must be 1..2^31"); return nullptr; }
     Pending* p = new Pending();
-    if (make_plan(kind, tablesizes, n_tables, world, budget_kmers, slice_log2_bytes > 0 ? slice_log2_bytes : 25, p->host)) { delete p; return nullptr; }
+    if (make_plan(kind, tablesizes, n_tables, world, budget_kmers, slice_log2_bytes > 0 ? slice_log2_bytes : default_slice_log2_bytes(kind), p->host)) { delete p; return nullptr; }
     gt_storage* st = storage_create(kind, tablesizes, n_tables, rank, world, p->host.own_lo.data() + (size_t)rank * n_tables,
                                     p->host.own_hi.data() + (size_t)rank * n_tables);
     if (!st) { delete p; return nullptr; }
@@ -1137,6 +1165,22 @@ extern "C" int gt_peer_close(void* ptr) {
     return 0;
 }
 
+// layout of a rank's inbox (peer transport): world bucket regions of R entries, then world overflow lists
+static uint64_t ovf_records() { return std::max<uint64_t>(16, env_u64("GT_OVF_RECORDS", 1u << 18)); }
+static uint64_t inbox_region_entries(const PlanHost& H, int rank) {
+    uint64_t R = 0;
+    for (int b = 0; b < H.nb; ++b)
+        if (H.owner[b] == rank) R += H.cap[b];
+    return R;
+}
+static uint64_t inbox_ovf_offset_bytes(const PlanHost& H, int rank) {
+    return ((uint64_t)H.world * inbox_region_entries(H, rank) * 4 + 15) / 16 * 16;
+}
+extern "C" uint64_t gt_storage_inbox_bytes(const gt_storage* st, int rank) {
+    if (!st || !st->pend || rank < 0 || rank >= st->world) return 0;
+    return inbox_ovf_offset_bytes(st->pend->host, rank) + (uint64_t)st->world * ovf_records() * 8;
+}
+
 extern "C" int gt_storage_attach_peers(gt_storage* st, int which, void* const* inbox_of_rank, void* fill_send,
                                         void* fill_recv) {
     if (ensure_ctx()) return -1;
@@ -1178,13 +1222,31 @@ extern "C" int gt_storage_attach_peers(gt_storage* st, int which, void* const* i
     for (int j = 0; j < n_owned; ++j) {
         const int b = owned[j];
         for (int q = 0; q < W; ++q)
-            items.push_back(ApplyItem{mine + (uint64_t)q * R[me] + in_region[b], fr + (size_t)q * n_owned + j, H.slot0[b], H.cap[b],
-                                      (uint32_t)H.table[b]});
+            items.push_back(ApplyItem{mine + (uint64_t)q * R[me] + in_region[b], fr + (size_t)q * (n_owned + 1) + j, H.slot0[b],
+                                      H.cap[b], (uint32_t)H.table[b]});
     }
     if (pending_set_items(p, items, which)) return -1;
     S.d_bfill = static_cast<uint32_t*>(fill_send);
     p->own_bfill = false;
-    CU(cudaMemset(S.d_bfill, 0, (size_t)nb * 4));
+    // overflow lists: mine in every owner's inbox (to post to), the world lists of my own inbox (to apply)
+    p->ovf_cap = (uint32_t)ovf_records();
+    p->count_stride = (uint32_t)n_owned + 1;
+    if (!p->d_bowner) {
+        std::vector<uint8_t> own(nb);
+        for (int b = 0; b < nb; ++b) own[b] = (uint8_t)H.owner[b];
+        CU(cudaMalloc(&p->d_bowner, nb));
+        CU(cudaMemcpy(p->d_bowner, own.data(), nb, cudaMemcpyHostToDevice));
+    }
+    std::vector<unsigned long long*> lists(W);
+    for (int q = 0; q < W; ++q)
+        lists[q] = reinterpret_cast<unsigned long long*>(static_cast<char*>(inbox_of_rank[q]) + inbox_ovf_offset_bytes(H, q)) +
+                   (uint64_t)me * p->ovf_cap;
+    CU(cudaMalloc(&S.d_ovf_ptr, W * sizeof(unsigned long long*)));
+    CU(cudaMemcpy(S.d_ovf_ptr, lists.data(), W * sizeof(unsigned long long*), cudaMemcpyHostToDevice));
+    S.my_ovf = reinterpret_cast<const unsigned long long*>(static_cast<const char*>(inbox_of_rank[me]) + inbox_ovf_offset_bytes(H, me));
+    S.ovf_counts = fr + n_owned;
+    S.fill_words = (uint32_t)(nb + W);
+    CU(cudaMemset(S.d_bfill, 0, (size_t)S.fill_words * 4));
     p->entries_total = (uint64_t)W * R[me];
     S.built = true;
     p->attached = true;
@@ -1282,8 +1344,8 @@ extern "C" int gt_storage_pending_info(gt_storage* st, uint64_t* info) {
     unsigned long long nd[2] = {0, 0};
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(nd, p->d_counters, 16, cudaMemcpyDeviceToHost));
-    if (nd[1]) return fail("sharded insert dropped %llu updates that overflowed a bucket of a slice held by another rank "
-                           "(skewed input: lower the k-mers per round)", nd[1]);
+    if (nd[1]) return fail("%llu updates overflowed both their bucket and the overflow / spill list (extremely skewed input: "
+                           "lower the k-mers per round or call)", nd[1]);
     info[0] = 1;
     info[1] = (uint64_t)p->host.nb;
     info[2] = (uint64_t)p->plan.shift;
@@ -1562,7 +1624,9 @@ extern "C" int gt_insert_hashes(gt_storage* st, const uint64_t* hashes, uint64_t
     if (st->world > 1) return fail("gt_insert_hashes: not available on a sharded storage");
     if (check_mode("gt_insert_hashes", mode)) return -1;
     if (is_new && mode == GT_MODE_BLIND) return fail("gt_insert_hashes: is_new needs GT_MODE_FAST or GT_MODE_EXACT");
-    if (mode != GT_MODE_BLIND && pending_flush_sync(st)) return -1;  // is_new must see every earlier insert
+    // is_new must see every earlier insert; and the saturating CAS of a counting storage must not run beside
+    // an optimistic apply (bucket.cuh, K2 for the counting storages)
+    if ((mode != GT_MODE_BLIND || st->kind != 0) && pending_flush_sync(st)) return -1;
     if (n == 0) return 0;
     CU(cudaSetDevice(g_ctx.device));
     const uint64_t chunk = 64ull << 20;  // hashes per chunk

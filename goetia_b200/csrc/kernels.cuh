@@ -732,6 +732,25 @@ __global__ void __launch_bounds__(256) k_count_occupied(const uint32_t* __restri
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, mine);
 }
 
+// Position-weighted checksum of a table: sum over 32-bit words of word * mix(index) mod 2^64 (mix = the
+// 64-bit finaliser of the word index, forced odd).  Order-independent to compute, sensitive to every bit and
+// to where it sits; used to compare multi-GB tables (two insert paths, shards vs whole) without moving them.
+__host__ __device__ __forceinline__ uint64_t checksum_weight(uint64_t i) {
+    uint64_t k = i + 0x9e3779b97f4a7c15ull;
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return k | 1ull;
+}
+__global__ void __launch_bounds__(256) k_checksum(const uint32_t* __restrict__ tbl, uint64_t n_words, uint64_t word0,
+                                                   unsigned long long* out) {
+    unsigned long long mine = 0;
+    for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words; w += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t x = tbl[w];
+        if (x) mine += (unsigned long long)x * checksum_weight(word0 + w);
+    }
+    for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, mine);
+}
+
 // BitStorage::update_from (bitstorage.cc:103-137): dst |= src
 __global__ void __launch_bounds__(256) k_or_tables(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint64_t n_words) {
     for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words; w += (uint64_t)gridDim.x * blockDim.x)

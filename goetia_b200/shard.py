@@ -171,12 +171,16 @@ class ShardedStorage:
                             "gt_storage_attach_exchange")
             self.x = self.sets[0]
         else:
-            self._perm = torch.as_tensor(plan.perm, dtype=torch.int64, device=dev)
-            self._fill_in = [plan.n_owned[q] for q in range(W)]
-            self._fill_out = [plan.n_owned[me]] * W
+            # fill_send = [bucket cursors (nb), overflow-list cursors per owner (W)]; what goes to owner q is
+            # the cursors of q's buckets followed by the overflow count for q
+            perm = np.concatenate([np.concatenate([plan.owned[q], [plan.nb + q]]) for q in range(W)]).astype(np.int64)
+            self._perm = torch.as_tensor(perm, dtype=torch.int64, device=dev)
+            self._fill_in = [plan.n_owned[q] + 1 for q in range(W)]
+            self._fill_out = [plan.n_owned[me] + 1] * W
+            self._n_fill = plan.nb + W
             self.fill_send, self.fill_recv, self._fx = [], [], []
             for w in range(2):
-                own = L.gt_peer_alloc(max(16, W * plan.region[me] * 4))
+                own = L.gt_peer_alloc(int(L.gt_storage_inbox_bytes(self._h, me)))
                 if not own:
                     raise _capi.GoetiaB200Error("gt_peer_alloc: " + _capi.last_error())
                 self._own_inbox.append(own)
@@ -197,11 +201,11 @@ class ShardedStorage:
                             raise _capi.GoetiaB200Error("gt_peer_open(rank %d): %s" % (q, _capi.last_error()))
                         self._peer_ptrs.append(pq)
                         ptrs[q] = pq
-                fs = torch.zeros(max(plan.nb, 1), dtype=torch.int32, device=dev)
-                fr = torch.zeros(max(W * plan.n_owned[me], 1), dtype=torch.int32, device=dev)
+                fs = torch.zeros(self._n_fill, dtype=torch.int32, device=dev)
+                fr = torch.zeros(W * (plan.n_owned[me] + 1), dtype=torch.int32, device=dev)
                 self.fill_send.append(fs)
                 self.fill_recv.append(fr)
-                self._fx.append(torch.zeros(max(plan.nb, 1), dtype=torch.int32, device=dev))
+                self._fx.append(torch.zeros(self._n_fill, dtype=torch.int32, device=dev))
                 _capi.check(L.gt_storage_attach_peers(self._h, w, ptrs, fs.data_ptr(), fr.data_ptr()),
                             "gt_storage_attach_peers")
             torch.cuda.synchronize()
@@ -245,9 +249,8 @@ class ShardedStorage:
                 # it must not complete before that set's k_apply has finished here.
                 if self._applied[w ^ 1] is not None:
                     self.stream.wait_event(self._applied[w ^ 1])
-                torch.index_select(self.fill_send[w][:plan.nb], 0, self._perm, out=self._fx[w][:plan.nb])
-                dist.all_to_all_single(self.fill_recv[w][:plan.world * plan.n_owned[self.rank]], self._fx[w][:plan.nb],
-                                       self._fill_out, self._fill_in, group=self.group)
+                torch.index_select(self.fill_send[w], 0, self._perm, out=self._fx[w])
+                dist.all_to_all_single(self.fill_recv[w], self._fx[w], self._fill_out, self._fill_in, group=self.group)
             ev = torch.cuda.Event()
             ev.record(self.stream)
         self.apply_stream.wait_event(ev)
@@ -331,6 +334,17 @@ class ShardedStorage:
             _capi.check(L.gt_storage_download_table(self._h, i, buf.ctypes.data), "gt_storage_download_table")
             out.append(buf)
         return out
+
+    def checksum(self, i):
+        """Checksum of the WHOLE table i: the ranks' part checksums add up (gt_storage_checksum is linear)."""
+        out = C.c_uint64(0)
+        self.synchronize()
+        _capi.check(_capi.lib().gt_storage_checksum(self._h, int(i), C.byref(out)), "gt_storage_checksum")
+        v = int(out.value)
+        t = self.torch.tensor([v & 0xFFFFFFFF, v >> 32], dtype=self.torch.int64, device=self.device)
+        self.dist.all_reduce(t, group=self.group)  # 32-bit halves: NCCL has no modular uint64 sum we can rely on
+        lo, hi = int(t[0].item()), int(t[1].item())
+        return (lo + (hi << 32)) & 0xFFFFFFFFFFFFFFFF
 
     def n_occupied_local(self):
         a = np.zeros(2, dtype=np.uint64)

@@ -128,6 +128,13 @@ class _Storage:
             out.append(buf)
         return out
 
+    def checksum(self, i):
+        """Position-weighted checksum of table i computed on the device (gt_storage_checksum)."""
+        import ctypes as C
+        out = C.c_uint64(0)
+        _capi.check(_capi.lib().gt_storage_checksum(self._h, int(i), C.byref(out)), "gt_storage_checksum")
+        return int(out.value)
+
     def reset(self):
         _capi.check(_capi.lib().gt_storage_reset(self._h), "gt_storage_reset")
 

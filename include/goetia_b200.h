@@ -101,6 +101,11 @@ int gt_storage_upload_table(gt_storage* st, int i, const uint8_t* host_src);
  * table 0 (number of non-zero slots), which is what the reference's counter equals. */
 int gt_storage_stats(gt_storage* st, uint64_t* n_unique, uint64_t* n_occupied);
 int gt_storage_set_n_unique(gt_storage* st, uint64_t n_unique);
+/* Position-weighted checksum of table i, computed in HBM: sum over the table's little-endian 32-bit
+ * words of word * weight(global word index) mod 2^64, weight(j) = fmix64(j + 0x9e3779b97f4a7c15) | 1
+ * (fmix64 = the MurmurHash3 finaliser).  Linear, so the parts of a sharded storage sum to the checksum
+ * of the reference's whole table; lets multi-GB tables be compared without moving them. */
+int gt_storage_checksum(gt_storage* st, int i, uint64_t* out);
 /* BitStorage::update_from (bitstorage.cc:103-137): dst |= src, same table sizes. */
 int gt_storage_update_from(gt_storage* dst, const gt_storage* src);
 /* Raw device pointer of table i (for peer mapping / torch interop). */
@@ -214,7 +219,8 @@ int gt_profile_get(double* ms3, uint64_t* n3);
  * gt_shard_plan: host arithmetic only (no GPU needed).  shift_nb[2] = {log2(slots per slice),
  * number of buckets}; per bucket: table, owner rank, first slot, slots, capacity in entries
  * per producer and round (arrays of >= 1024 elements); own_lo/own_hi[world * n_tables] = slot
- * range of table t on rank r at [r * n_tables + t].  slice_log2_bytes <= 0 selects 32 MB. */
+ * range of table t on rank r at [r * n_tables + t].  slice_log2_bytes <= 0 selects the default (32 MB of
+ * table, 64 MB for ByteStorage). */
 int gt_shard_plan(int kind, const uint64_t* tablesizes, int n_tables, int world, uint64_t budget_kmers,
                   int slice_log2_bytes, int32_t* shift_nb, int32_t* table, int32_t* owner, uint64_t* slot0,
                   uint64_t* slots, uint32_t* cap, uint64_t* own_lo, uint64_t* own_hi);
@@ -254,10 +260,18 @@ int gt_peer_free(void* ptr);
 int gt_peer_export(void* ptr, uint8_t handle[64]);
 void* gt_peer_open(const uint8_t handle[64]);
 int gt_peer_close(void* ptr);
+/* Bytes of rank `rank`'s inbox (one per buffer set): the world bucket regions followed by world
+ * overflow lists (GT_OVF_RECORDS, default 2^18, records of 8 bytes each).  An update whose bucket is
+ * full (heavily duplicated k-mers) cannot be applied by the producer when the slice is foreign; it is
+ * posted to the producer's overflow list in the owner's inbox as a full (table, slot) record and
+ * applied there, so correctness does not depend on bucket capacities here either. */
+uint64_t gt_storage_inbox_bytes(const gt_storage* st, int rank);
 /* inbox_of_rank[world]: device pointers valid in THIS process (entry `rank` = this rank's own
- * inbox from gt_peer_alloc, the others from gt_peer_open).  fill_send [n_buckets], fill_recv
- * [world * n_owned] as for gt_storage_attach_exchange; the caller moves fill_send -> fill_recv
- * (owner-major) after k_bucket, e.g. with one small all-to-all. */
+ * inbox of gt_storage_inbox_bytes bytes from gt_peer_alloc, the others from gt_peer_open).
+ * fill_send [n_buckets + world]: bucket cursors, then the overflow-list cursors per owner rank;
+ * fill_recv [world * (n_owned + 1)]: [q] = what rank q produced for this rank's n_owned buckets, then
+ * its overflow count.  The caller moves fill_send -> fill_recv (owner-major) after k_bucket, e.g. with
+ * one small all-to-all. */
 int gt_storage_attach_peers(gt_storage* st, int which, void* const* inbox_of_rank, void* fill_send,
                             void* fill_recv);
 /* Storage::query restricted to the slots this rank holds (routed queries on a sharded storage):

@@ -63,7 +63,8 @@ def main():
     my_o = offsets[r0:r1 + 1] - offsets[r0]
     # gt_insert_sequences_dev bounds a batch by its bases; x3 because these reads are heavily duplicated
     # (a 4 kb genome), so bucket loads are far from the uniform share the capacities are sized for
-    budget = max(1024, per * 100 * 3)
+    # (SHARD_BUDGET_X=1 makes buckets of foreign slices overflow: the overflow lists of the peer transport)
+    budget = max(1024, per * 100 * int(os.environ.get("SHARD_BUDGET_X", "3")))
     slice_log2 = int(os.environ.get("SHARD_SLICE_LOG2", "10"))
 
     if mode == "cpu":

@@ -208,3 +208,36 @@ def test_big_table_reducers(gb, monkeypatch, x):
     for a, b in zip(g.get_raw(), ref.tables()):
         assert a.size == b.size and Port.fnv1a(a) == Port.fnv1a(b)
     g.S.close()
+
+
+@pytest.mark.parametrize("kind,_n", [(1, "ByteStorage"), (2, "NibbleStorage")])
+@pytest.mark.parametrize("cas", ["0", "1"])
+def test_bucketed_counting_saturation(gb, forced, monkeypatch, kind, _n, cas):
+    """Counting storages are applied optimistically (plain atomic adds; slices where an add met a counter at its
+    maximum are undone and replayed with the saturating CAS -- bucket.cuh, K2 for the counting storages).  Deep
+    coverage drives many counters through their maximum inside the buckets; tables must still equal the oracle's
+    min(max, hits) byte for byte, over several applies, and the plain CAS apply (GT_APPLY_CAS=1) must agree."""
+    forced(slice_log2=13, entries=1 << 24)
+    monkeypatch.setenv("GT_APPLY_CAS", cas)
+    K = 21
+    sizes = gb.get_n_primes_near_x(4, 700_001)
+    bases, offsets = genome_reads(30000, 100, 2500, seed=31)  # ~1000x coverage of 2.5 kb: counts far past 255
+    g = make_graph(gb, kind, 1, K, sizes)
+    ref = Port(kind, 1, K, sizes)
+    for _ in range(2):
+        for r0 in range(0, 30000, 10000):  # three calls per pass: several stores / applies
+            b = bases[int(offsets[r0]):int(offsets[r0 + 10000])]
+            o = offsets[r0:r0 + 10001] - offsets[r0]
+            g.insert_sequences(b, o, mode=0)
+            ref.insert_reads(b, o)
+    g.flush()
+    assert g.S.pending_info()["built"]
+    assert_tables_equal(g.get_raw(), ref.tables())
+    q = g.query_sequences(bases[:300], offsets[:4])
+    assert int(q.max()) == (255 if kind == 1 else 15)
+    # mixed: unique reads on top (no saturation in most slices), then the tables once more
+    ub, uo = synth_reads(5000, 100, seed=32)
+    g.insert_sequences(ub, uo, mode=0)
+    ref.insert_reads(ub, uo)
+    assert_tables_equal(g.get_raw(), ref.tables())
+    ref.close()

@@ -96,3 +96,18 @@ def test_sharded_insert_nccl(kind, transport):
                                              "SHARD_ROUNDS": "3", "SHARD_TRANSPORT": transport})
     assert rcs == [0] * world, "\n".join(outs)
     assert "tables bit-exact" in outs[0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", [0, 1])
+def test_sharded_insert_foreign_bucket_overflow(kind):
+    """Heavily duplicated reads with capacities sized for the uniform share: buckets of foreign slices overflow
+    and the excess travels through the overflow lists (bucket.cuh, post_foreign) -- tables stay bit-exact."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    rcs, outs = launch("cuda", kind, 2, {"SHARD_TABLE_X": "40000000", "SHARD_READS": "40000", "SHARD_SLICE_LOG2": "16",
+                                         "SHARD_ROUNDS": "2", "SHARD_TRANSPORT": "p2p", "SHARD_BUDGET_X": "1"})
+    assert rcs == [0, 0], "\n".join(outs)
+    assert "tables bit-exact" in outs[0]

@@ -57,3 +57,20 @@ def assert_tables_equal(gpu_tables, cpu_tables):
             bad = np.nonzero(a != b)[0]
             raise AssertionError("table %d differs at %d bytes, first at %d: gpu=%d cpu=%d"
                                  % (i, bad.size, bad[0], a[bad[0]], b[bad[0]]))
+
+
+def table_checksum(table_bytes):
+    """numpy rendering of gt_storage_checksum (include/goetia_b200.h): sum of word * weight(index) mod 2^64."""
+    b = np.ascontiguousarray(table_bytes, dtype=np.uint8)
+    if b.size % 4:
+        b = np.concatenate([b, np.zeros(4 - b.size % 4, dtype=np.uint8)])
+    words = b.view("<u4").astype(np.uint64)
+    with np.errstate(over="ignore"):
+        k = np.arange(words.size, dtype=np.uint64) + np.uint64(0x9e3779b97f4a7c15)
+        k ^= k >> np.uint64(33)
+        k *= np.uint64(0xff51afd7ed558ccd)
+        k ^= k >> np.uint64(33)
+        k *= np.uint64(0xc4ceb9fe1a85ec53)
+        k ^= k >> np.uint64(33)
+        k |= np.uint64(1)
+        return int((words * k).sum(dtype=np.uint64))
