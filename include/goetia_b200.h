@@ -220,7 +220,7 @@ int gt_profile_get(double* ms3, uint64_t* n3);
  * number of buckets}; per bucket: table, owner rank, first slot, slots, capacity in entries
  * per producer and round (arrays of >= 1024 elements); own_lo/own_hi[world * n_tables] = slot
  * range of table t on rank r at [r * n_tables + t].  slice_log2_bytes <= 0 selects the default (32 MB of
- * table, 64 MB for ByteStorage). */
+ * table, 64 MB for the counting storages). */
 int gt_shard_plan(int kind, const uint64_t* tablesizes, int n_tables, int world, uint64_t budget_kmers,
                   int slice_log2_bytes, int32_t* shift_nb, int32_t* table, int32_t* owner, uint64_t* slot0,
                   uint64_t* slots, uint32_t* cap, uint64_t* own_lo, uint64_t* own_hi);
