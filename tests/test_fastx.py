@@ -49,9 +49,22 @@ def check(seqs, stats, want):
     assert str(Port.fnv1a(lens.view(np.uint8))) == want["len_fnv"]
 
 
+@pytest.fixture(params=["serial", "parallel"])
+def engine(request, monkeypatch):
+    """Both parser engines on every case.  The parallel one (uncompressed files read batch-wise) is forced onto
+    tiny files with 997-byte chunks, so that most speculative chunk starts are wrong and get re-parsed."""
+    if request.param == "serial":
+        monkeypatch.setenv("GT_FASTX_THREADS", "1")
+    else:
+        monkeypatch.setenv("GT_FASTX_THREADS", "4")
+        monkeypatch.setenv("GT_FASTX_CHUNK_BYTES", "997")
+        monkeypatch.setenv("GT_FASTX_PARALLEL_MIN_BYTES", "0")
+    return request.param
+
+
 @pytest.mark.parametrize("gz", [False, True])
 @pytest.mark.parametrize("case", [c for c in cases()], ids=lambda c: c[0])
-def test_parser_matches_reference(tmp_path, case, gz):
+def test_parser_matches_reference(tmp_path, case, gz, engine):
     from goetia_b200 import parsing
     name, data, min_length, strict = case
     fn = write_case(str(tmp_path), name, data, gz)
