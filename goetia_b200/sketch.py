@@ -145,6 +145,59 @@ class Sketch:
         c.merge(self)
         return c
 
+    # -- streaming: what `goetia sketch sourmash` does around the sketch (goetia/cli/signature_runner.py:131-157:
+    # a snapshot every `interval` k-mers and the distance between consecutive snapshots) -----------------------
+    def stream_fastx(self, parser_or_filename, interval=1_000_000, strict=False, min_length=0, batch_bases=64 << 20):
+        """Generator over the intervals of a FASTX stream: yields dicts ``{t, sequences, size, similarity,
+        distance}`` -- t = k-mers consumed so far (the processors' clock), size = hashes in the sketch,
+        similarity = Jaccard of this snapshot with the previous one (None for the first), distance = 1 - it.
+        Whole intervals are sketched in one device call each; the last, partial interval is reported too."""
+        from .parsing import FastxParser
+        own = not isinstance(parser_or_filename, FastxParser)
+        parser = FastxParser(parser_or_filename, strict, min_length) if own else parser_or_filename
+        prev, t, n_seqs, since = None, 0, 0, 0
+        try:
+            while True:
+                # a batch holds about one interval's worth of k-mers (reads carry len - K + 1 each)
+                bases, offsets = parser.next_batch(batch_bases, max_reads=max(1, interval // 64))
+                done = offsets.size == 1
+                if not done:
+                    # cut the batch where the interval fills up
+                    kmers = np.maximum((offsets[1:] - offsets[:-1]).astype(np.int64) - self.K + 1, 0)
+                    cum = np.cumsum(kmers)
+                    r0 = 0
+                    while r0 < kmers.size:
+                        room = interval - since
+                        base = cum[r0 - 1] if r0 else 0
+                        r1 = int(np.searchsorted(cum, base + room, side="left")) + 1
+                        r1 = min(max(r1, r0 + 1), kmers.size)
+                        b = bases[int(offsets[r0]):int(offsets[r1])]
+                        o = offsets[r0:r1 + 1] - offsets[r0]
+                        nk = self.insert_sequences(b, o)
+                        t += nk
+                        since += nk
+                        n_seqs += r1 - r0
+                        r0 = r1
+                        if since >= interval:
+                            snap = self.copy()
+                            sim = snap.jaccard(prev) if prev is not None else None
+                            yield {"t": t, "sequences": n_seqs, "size": snap.size(), "similarity": sim,
+                                   "distance": None if sim is None else 1.0 - sim}
+                            if prev is not None:
+                                prev.close()
+                            prev, since = snap, 0
+                if done:
+                    if since:
+                        sim = self.jaccard(prev) if prev is not None else None
+                        yield {"t": t, "sequences": n_seqs, "size": self.size(), "similarity": sim,
+                               "distance": None if sim is None else 1.0 - sim}
+                    break
+        finally:
+            if prev is not None:
+                prev.close()
+            if own:
+                parser.close()
+
     # -- multi-GPU: every rank sketches its shard of the reads; the sketch of the whole set is the
     # union (SURVEY.md section 8e) ----------------------------------------------------------------
     def allgather_merge(self, group=None):

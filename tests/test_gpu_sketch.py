@@ -170,3 +170,37 @@ def test_full_size_properties(gb):
     hb = d_b[:20000 * L].cpu().numpy()
     o.add_reads(hb, np.arange(20001, dtype=np.uint64) * np.uint64(L))
     assert set(o.mins().tolist()) <= set(m1.tolist())
+
+
+def test_stream_fastx_intervals(gb, tmp_path):
+    """The streaming loop of `goetia sketch sourmash` (signature_runner.py:131-157): snapshots every `interval`
+    k-mers; at every snapshot the hash set equals the oracle's after the same prefix of reads, and the reported
+    similarity is the Jaccard of consecutive oracle snapshots."""
+    import os
+    from tests.util import genome_reads, read_str
+    K, n_reads, L, interval = 21, 3000, 100, 40_000
+    bases, offsets = genome_reads(n_reads, L, 60_000, seed=8)
+    fn = os.path.join(str(tmp_path), "s.fa")
+    with open(fn, "w") as f:
+        for r in range(n_reads):
+            f.write(">r%d\n%s\n" % (r, read_str(bases, offsets, r)))
+    g = _sk(gb, 0, K, 50)
+    snaps = list(g.stream_fastx(fn, interval=interval))
+    per = L - K + 1
+    assert snaps[-1]["t"] == n_reads * per and snaps[-1]["sequences"] == n_reads
+    assert len(snaps) == -(-n_reads // -(-interval // per))  # every interval closes at the read that fills it
+    o = PortSketch(0, K, 42, scaled=50)
+    done, prev = 0, None
+    for s in snaps:
+        n = s["sequences"]
+        assert s["t"] == n * per
+        o.add_reads(bases[int(offsets[done]):int(offsets[n])], offsets[done:n + 1] - offsets[done])
+        done = n
+        cur = set(o.mins().tolist())
+        assert s["size"] == len(cur)
+        if prev is None:
+            assert s["similarity"] is None
+        else:
+            assert abs(s["similarity"] - len(cur & prev) / len(cur | prev)) < 1e-12
+        prev = cur
+    assert np.array_equal(g.mins(), o.mins())
