@@ -461,8 +461,9 @@ k_apply(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ items
 //   k_apply_red<UNDO>  subtracts every update again -- exact whatever the wraps did to neighbouring counters,
 //                      because add and subtract cancel mod 2^32;
 //   k_apply(only_failed) replays the updates with the saturating CAS.
-// NibbleStorage saturates routinely (that is what 4-bit counters are for), so its default stays the CAS apply;
-// GT_APPLY_CAS=0 / 1 forces the optimistic / the CAS apply for either storage.
+// A slice that failed is remembered as hot and goes straight to the CAS replay in the following applies (4-bit
+// counters saturate routinely once a table fills up); every 8th apply clears the flags and tries again.
+// GT_APPLY_CAS=1 forces the plain CAS apply.
 // Nothing else writes the tables meanwhile: k_bucket parks its own overflow (ProducePlan::own_spill) and the direct
 // writers are ordered against the apply stream (direct_begin / direct_end).  Final bytes are bit-exact.
 // Items of one slice are consecutive (items_per_slice = ranks that produced for it): slice = item / items_per_slice.
@@ -513,10 +514,12 @@ __global__ void __launch_bounds__(256) k_slice_sums(const __grid_constant__ Tabl
 
 // UNDO = false: the optimistic pass.  UNDO = true: subtract the same updates again, only in the slices whose
 // check failed (delta != 0 after k_slice_sums<+1>); delta is left untouched so that the replay sees it too.
+// hot[slice] != 0: the slice saturated in a recent apply; it is left to the CAS replay straight away (no adds,
+// nothing to undo) until the flags are cleared again (every 8th apply retries the optimistic path).
 template <int KIND, bool UNDO>
 __global__ void __launch_bounds__(AP_THREADS)
 k_apply_red(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ items, const uint32_t* __restrict__ chunk_start,
-            int n_items, int items_per_slice, unsigned long long* __restrict__ delta) {
+            int n_items, int items_per_slice, unsigned long long* __restrict__ delta, const uint32_t* __restrict__ hot) {
     static_assert(KIND == 1 || KIND == 2, "counting storages only");
     __shared__ uint32_t s_b;
     if (threadIdx.x == 0) {
@@ -529,6 +532,7 @@ k_apply_red(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ i
     }
     __syncthreads();
     const uint32_t b = s_b;
+    if (__ldcg(hot + b / (uint32_t)items_per_slice) != 0u) return;
     if (UNDO && __ldcg(delta + b / (uint32_t)items_per_slice) == 0ull) return;
     const ApplyItem it = items[b];
     const uint32_t fill = min(__ldcg(it.fill), it.cap);
@@ -559,6 +563,15 @@ k_apply_red(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ i
         for (int o = 16; o; o >>= 1) applied += __shfl_down_sync(0xffffffffu, applied, o);
         if ((threadIdx.x & 31) == 0 && applied) atomicAdd(delta + b / (uint32_t)items_per_slice, 0ull - (unsigned long long)applied);
     }
+}
+
+// after the undo pass: slices that failed the check become hot; hot slices (old and new) are what the replay applies
+__global__ void __launch_bounds__(256) k_mark_hot(unsigned long long* __restrict__ delta, uint32_t* __restrict__ hot, int n_slices) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slices) return;
+    const uint32_t h = (hot[s] != 0u || delta[s] != 0ull) ? 1u : 0u;
+    hot[s] = h;
+    delta[s] = h;
 }
 
 // Overflow lists received from the peers (rare path): world lists of up to `cap` (table, slot) records.
