@@ -498,9 +498,12 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
         copy_stream = torch.cuda.Stream()
         torch.cuda.synchronize()
 
+        pieces = max(1, int(os.environ.get("GT_BENCH_E2E_PIECES", "4")))
+
         def step_host():
-            # H2D of round i+1 (copy stream) overlaps pack/hash/bucket of round i (compute stream) and k_apply of
-            # round i-1 (apply stream); one result read-back (the k-mer count) at the end of the step
+            # Every round travels in `pieces` H2D copies (copy stream); pack/hash/bucket of a piece (compute stream)
+            # starts as soon as it has landed, so only the first piece of a step is exposed.  The exchange and
+            # k_apply (apply stream) stay per round.  One result read-back (the k-mer count) ends the step.
             consumed = [None, None]
             with torch.cuda.stream(st.stream):
                 d_total.zero_()
@@ -509,14 +512,20 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
                 with torch.cuda.stream(copy_stream):
                     if consumed[i & 1] is not None:
                         copy_stream.wait_event(consumed[i & 1])
-                    d[:h.numel()].copy_(h, non_blocking=True)
                     do.copy_(host_offs, non_blocking=True)
-                    ready = torch.cuda.Event()
-                    ready.record(copy_stream)
-                st.stream.wait_event(ready)
-                if n:
-                    st.bucket_sequences_dev_async(_capi.SHIFTER_CAN, K, d.data_ptr(), do.data_ptr(), n, n * read_len,
-                                                  d_total.data_ptr())
+                # piece boundaries on multiples of 16 reads: the _dev entry points want 16-byte-aligned base pointers
+                per_piece = (-(-max(n, 1) // pieces) + 15) // 16 * 16
+                for r0 in range(0, max(n, 1), per_piece):
+                    r1 = min(max(n, 1), r0 + per_piece)
+                    with torch.cuda.stream(copy_stream):
+                        d[r0 * read_len:r1 * read_len].copy_(h[r0 * read_len:r1 * read_len], non_blocking=True)
+                        ready = torch.cuda.Event()
+                        ready.record(copy_stream)
+                    st.stream.wait_event(ready)
+                    if n:
+                        # equal-length reads: the first r1-r0+1 offsets describe any piece
+                        st.bucket_sequences_dev_async(_capi.SHIFTER_CAN, K, d.data_ptr() + r0 * read_len, do.data_ptr(),
+                                                      r1 - r0, (r1 - r0) * read_len, d_total.data_ptr())
                 free = torch.cuda.Event()
                 free.record(st.stream)
                 consumed[i & 1] = free
@@ -538,7 +547,7 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
         e2e = {"value": kmers_per_step * args.steps / dts, "unit": "k-mers/s",
                "h2d_bytes_per_step": int(sum(h.numel() for h in hosts) + rounds * host_offs.numel() * 8) * world,
                "d2h_bytes_per_step": 8 * rounds * world, "ms_per_step": dts * 1e3 / args.steps,
-               "api": "ShardedStorage: pinned host ASCII -> H2D -> bucket (+ exchange, transport %s) -> apply (per rank)" % st.transport}
+               "api": "ShardedStorage: pinned host ASCII -> H2D in %d pieces per round -> bucket (+ exchange, transport %s) -> apply (per rank)" % (pieces, st.transport)}
 
     if rank == 0:
         peak, peak_src = measured_peak()

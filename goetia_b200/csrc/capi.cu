@@ -676,6 +676,10 @@ extern "C" void gt_batch_destroy(gt_batch* b) {
 }
 
 extern "C" gt_batch* gt_batch_pack_dev(const void* d_bases, const void* d_offsets, uint64_t n_reads, uint64_t n_bases) {
+    if ((reinterpret_cast<uintptr_t>(d_bases) & 15) || (reinterpret_cast<uintptr_t>(d_offsets) & 7)) {
+        fail("gt_batch_pack_dev: d_bases must be 16-byte aligned and d_offsets 8-byte aligned");
+        return nullptr;
+    }
     if (ensure_ctx()) return nullptr;
     if (n_reads >= (1ull << 32)) { fail("gt_batch_pack_dev: too many reads"); return nullptr; }
     gt_batch* b = batch_alloc(n_reads, n_bases);
@@ -961,6 +965,8 @@ static int insert_sequences_dev_queue(gt_storage* st, int shifter, int K, const 
     if (n_reads >= (1ull << 32)) return fail("gt_insert_sequences_dev: more than 2^32-1 reads in one call");
     if (n_reads == 0) return 0;
     if (!d_bases || !d_offsets) return fail("gt_insert_sequences_dev: NULL device pointer");
+    if ((reinterpret_cast<uintptr_t>(d_bases) & 15) || (reinterpret_cast<uintptr_t>(d_offsets) & 7))
+        return fail("gt_insert_sequences_dev: d_bases must be 16-byte aligned and d_offsets 8-byte aligned");
     CU(cudaSetDevice(g_ctx.device));
     if (mode != GT_MODE_BLIND && pending_flush_sync(st)) return -1;
     // pack into slot 0's buffers on the compute stream (everything here is stream-ordered on it)

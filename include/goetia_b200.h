@@ -20,6 +20,7 @@
  *     "_dev" entry points take device pointers already resident in HBM.  The library runs on
  *     its own non-blocking streams (or the ones given to gt_set_compute_stream): whatever
  *     produced those buffers must have completed, or be ordered before the call on that stream.
+ *     d_bases must be 16-byte aligned (the packer reads it with 16 B loads), d_offsets 8-byte.
  *   - sequences travel as one concatenated byte buffer `bases` plus `offsets[n_reads+1]`
  *     (read r = bases[offsets[r] .. offsets[r+1])).  Per read the semantics are those of
  *     FastxParser<DNA_SIMPLE> + InserterProcessor (parsing/readers.hh:150-219,

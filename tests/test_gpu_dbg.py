@@ -277,3 +277,15 @@ def test_sequence_overloads(gb, kind, _n):
         assert counts == want
         assert {h.value() for h in new} == {h.value() for h, c in zip(hs, want) if c == 0}
     ref.close()
+
+
+def test_dev_entry_points_reject_misaligned_pointers(gb):
+    """The _dev entry points read the bases with 16 B loads: a misaligned base pointer is an error, not a fault."""
+    import torch
+    g = make_graph(gb, 0, 1, 21, gb.get_n_primes_near_x(4, 100_003))
+    bases = torch.full((4096,), 65, dtype=torch.uint8, device="cuda")
+    offs = torch.tensor([0, 100], dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    with pytest.raises(gb.GoetiaB200Error):
+        g.insert_sequences_dev(bases.data_ptr() + 4, offs.data_ptr(), 1, 100, mode=0)
+    assert g.insert_sequences_dev(bases.data_ptr() + 16, offs.data_ptr(), 1, 100, mode=0) == 80
