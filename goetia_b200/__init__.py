@@ -13,6 +13,6 @@ from .storage import BitStorage, ByteStorage, NibbleStorage, get_n_primes_near_x
 from .dbg import dBG  # noqa: F401
 from .sketch import SourmashSketch  # noqa: F401
 from .parsing import FastxParser, Record  # noqa: F401
-from .filters import DiginormFilter, FilterProcessor  # noqa: F401
+from .filters import DiginormFilter, FilterProcessor, StreamingSolidFilter  # noqa: F401
 
 __version__ = "0.1.0"

@@ -52,6 +52,49 @@ class DiginormFilter:
         return bool(keep[0]), len(sequence) - self.K + 1
 
 
+class StreamingSolidFilter:
+    """``StreamingSolidFilter[dBG].Filter`` (include/goetia/solidifier.hh:33-77): a read passes when fewer than
+    ``1 - min_prop_solid`` of its k-mers have an insert_and_query count below ``solid_threshold``.  The counts are
+    the reference's serial ones (each k-mer sees the earlier k-mers of the read: dbg.hh:327-340), so this filter
+    runs on the per-k-mer latency path; it is here for API completeness, not throughput."""
+
+    def __init__(self, graph, min_prop_solid=0.75, solid_threshold=1):
+        self.graph, self.K = graph, graph.K
+        self.min_prop_solid, self.solid_threshold = float(min_prop_solid), int(solid_threshold)
+
+    @classmethod
+    def build(cls, graph, min_prop_solid=0.75, solid_threshold=1):
+        return cls(graph, min_prop_solid, solid_threshold)
+
+    def filter_sequence(self, sequence):
+        counts = self.graph.insert_and_query_sequence(sequence)
+        n_kmers = len(sequence) - self.K + 1
+        n_not_solid = sum(1 for c in counts if c < self.solid_threshold)
+        # arithmetic as the reference writes it (solidifier.hh:68): a float quotient against a double difference
+        # whose subtrahend is the float member min_prop_solid
+        if float(np.float32(n_not_solid) / np.float32(n_kmers)) >= 1.0 - float(np.float32(self.min_prop_solid)):
+            return False, n_kmers
+        return True, n_kmers
+
+    def filter_sequences(self, bases, offsets):
+        """Reads one after the other (the serial semantics do not batch); -> (keep, k-mers judged)."""
+        bases, offsets = _capi.as_reads(bases, offsets)
+        n = offsets.size - 1
+        keep = np.zeros(n, dtype=np.uint8)
+        judged = 0
+        for r in range(n):
+            seq = bases[int(offsets[r]):int(offsets[r + 1])].tobytes().decode("ascii")
+            if len(seq) < self.K:
+                continue  # SequenceLengthException, swallowed by the processor (processors.hh:395-403)
+            try:
+                ok, nk = self.filter_sequence(seq)
+            except ValueError:
+                continue  # InvalidCharacterException, swallowed likewise
+            keep[r] = 1 if ok else 0
+            judged += nk
+        return keep, judged
+
+
 class FilterProcessor:
     """FilterProcessor<Filter>: stream a FASTX file through the filter, write the passing records."""
 

@@ -84,3 +84,26 @@ def test_filter_processor_end_to_end(gb, tmp_path):
     assert names == ["r%d" % r for r in range(n_reads) if want[r]]
     assert proc.n_passed == int(want.sum())
     ref.close()
+
+
+def test_streaming_solid_filter(gb):
+    """StreamingSolidFilter::Filter::filter_sequence (solidifier.hh:58-76) replayed on the oracle's
+    insert_and_query_sequence."""
+    kind, K = 1, 21
+    sizes = gb.get_n_primes_near_x(4, 200_003)
+    bases, offsets = genome_reads(60, 70, 400, seed=4)  # overlapping reads: later ones are mostly solid
+    g = make_graph(gb, kind, 1, K, sizes)
+    f = gb.StreamingSolidFilter.build(g, 0.6, 2)
+    ref = Port(kind, 1, K, sizes)
+    want = []
+    for r in range(60):
+        s = read_str(bases, offsets, r)
+        counts = ref.insert_and_query_sequence(s)
+        n_not = int((counts < 2).sum())
+        want.append(0 if float(np.float32(n_not) / np.float32(len(s) - K + 1)) >= 1.0 - float(np.float32(0.6)) else 1)
+    keep, judged = f.filter_sequences(bases, offsets)
+    assert keep.tolist() == want and 0 < sum(want) < 60
+    assert judged == 60 * (70 - K + 1)
+    for a, b in zip(g.get_raw(), ref.tables()):
+        assert np.array_equal(a, b)
+    ref.close()
