@@ -79,6 +79,8 @@ SIGNATURES = {
     "gt_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gt_peer_open": (C.c_void_p, [C.c_void_p]),
     "gt_peer_close": (C.c_int, [C.c_void_p]),
+    "gt_shard_peer_layout": (C.c_int, [C.c_int, u64p, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
     "gt_storage_inbox_bytes": (C.c_uint64, [C.c_void_p, C.c_int]),
     "gt_storage_attach_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gt_query_hashes_local_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),

@@ -1187,6 +1187,34 @@ extern "C" uint64_t gt_storage_inbox_bytes(const gt_storage* st, int rank) {
     return inbox_ovf_offset_bytes(st->pend->host, rank) + (uint64_t)st->world * ovf_records() * 8;
 }
 
+// The inbox layout of the peer transport as host arithmetic (no GPU): what gt_storage_attach_peers lays out.
+static void peer_layout(const PlanHost& H, std::vector<uint64_t>& R, std::vector<uint64_t>& in_region) {
+    R.assign(H.world, 0);
+    in_region.assign(H.nb, 0);
+    for (int b = 0; b < H.nb; ++b) {
+        in_region[b] = R[H.owner[b]];
+        R[H.owner[b]] += H.cap[b];
+    }
+}
+extern "C" int gt_shard_peer_layout(int kind, const uint64_t* tablesizes, int n_tables, int world, uint64_t budget_kmers,
+                                    int slice_log2_bytes, uint64_t* region_entries, uint64_t* in_region,
+                                    uint64_t* ovf_offset_bytes, uint64_t* inbox_bytes) {
+    if (kind < 0 || kind > 2 || !tablesizes || n_tables < 1 || n_tables > MAX_TABLES || world < 1)
+        return fail("gt_shard_peer_layout: bad argument");
+    PlanHost P;
+    if (make_plan(kind, tablesizes, n_tables, world, budget_kmers, slice_log2_bytes > 0 ? slice_log2_bytes : default_slice_log2_bytes(kind), P)) return -1;
+    std::vector<uint64_t> R, ir;
+    peer_layout(P, R, ir);
+    for (int q = 0; q < world; ++q) {
+        if (region_entries) region_entries[q] = R[q];
+        if (ovf_offset_bytes) ovf_offset_bytes[q] = inbox_ovf_offset_bytes(P, q);
+        if (inbox_bytes) inbox_bytes[q] = inbox_ovf_offset_bytes(P, q) + (uint64_t)world * ovf_records() * 8;
+    }
+    if (in_region)
+        for (int b = 0; b < P.nb; ++b) in_region[b] = ir[b];
+    return P.nb;
+}
+
 extern "C" int gt_storage_attach_peers(gt_storage* st, int which, void* const* inbox_of_rank, void* fill_send,
                                         void* fill_recv) {
     if (ensure_ctx()) return -1;
@@ -1201,12 +1229,10 @@ extern "C" int gt_storage_attach_peers(gt_storage* st, int which, void* const* i
     for (int q = 0; q < W; ++q)
         if (!inbox_of_rank[q]) return fail("gt_storage_attach_peers: inbox of rank %d is NULL", q);
     std::vector<int> owned;
-    std::vector<uint64_t> R(W, 0), in_region(nb, 0);
-    for (int b = 0; b < nb; ++b) {
-        in_region[b] = R[H.owner[b]];
-        R[H.owner[b]] += H.cap[b];
+    std::vector<uint64_t> R, in_region;
+    peer_layout(H, R, in_region);
+    for (int b = 0; b < nb; ++b)
         if (H.owner[b] == me) owned.push_back(b);
-    }
     const int n_owned = (int)owned.size();
     if (!p->attached && pending_alloc_common(st, p, n_owned * W)) return -1;
     if (which == 1) {

@@ -32,6 +32,7 @@ class ShardPlan:
     def __init__(self, kind, sizes, world, budget_kmers, slice_log2_bytes=0):
         L = _capi.load()
         self.kind, self.world, self.budget_kmers = int(kind), int(world), int(budget_kmers)
+        self._slice_log2_bytes = int(slice_log2_bytes)
         self.sizes = np.ascontiguousarray(sizes, dtype=np.uint64)
         n = self.sizes.size
         shift_nb = np.zeros(2, dtype=np.int32)
@@ -60,6 +61,27 @@ class ShardPlan:
         self.in_region = np.zeros(nb, dtype=np.int64)  # offset of bucket b inside its owner's region
         for o in self.owned:
             self.in_region[o] = np.cumsum(self.cap[o]) - self.cap[o]
+
+    def peer_layout(self):
+        """gt_shard_peer_layout: the inbox layout of the peer transport (what gt_storage_attach_peers lays out).
+        -> dict(region[world], in_region[nb], ovf_offset_bytes[world], inbox_bytes[world])."""
+        L = _capi.load()
+        W = self.world
+        region = np.zeros(W, dtype=np.uint64)
+        in_region = np.zeros(max(self.nb, 1), dtype=np.uint64)
+        ovf = np.zeros(W, dtype=np.uint64)
+        inbox = np.zeros(W, dtype=np.uint64)
+        _capi.check(L.gt_shard_peer_layout(self.kind, self.sizes.ctypes.data_as(_capi.u64p), self.sizes.size, W,
+                                           self.budget_kmers, self._slice_log2_bytes, region.ctypes.data,
+                                           in_region.ctypes.data, ovf.ctypes.data, inbox.ctypes.data),
+                    "gt_shard_peer_layout")
+        return {"region": region.astype(np.int64), "in_region": in_region[:self.nb].astype(np.int64),
+                "ovf_offset_bytes": ovf.astype(np.int64), "inbox_bytes": inbox.astype(np.int64)}
+
+    def fill_perm(self):
+        """Gather order of the peer transport's fill exchange: fill_send = [bucket cursors (nb), overflow
+        cursors per owner (world)]; owner q receives the cursors of its buckets, then the overflow count."""
+        return np.concatenate([np.concatenate([self.owned[q], [self.nb + q]]) for q in range(self.world)]).astype(np.int64)
 
     def outbox_offsets(self, me):
         """(offset of every bucket in rank `me`'s outbox, total entries, entries destined to peers)."""
@@ -173,8 +195,7 @@ class ShardedStorage:
         else:
             # fill_send = [bucket cursors (nb), overflow-list cursors per owner (W)]; what goes to owner q is
             # the cursors of q's buckets followed by the overflow count for q
-            perm = np.concatenate([np.concatenate([plan.owned[q], [plan.nb + q]]) for q in range(W)]).astype(np.int64)
-            self._perm = torch.as_tensor(perm, dtype=torch.int64, device=dev)
+            self._perm = torch.as_tensor(plan.fill_perm(), dtype=torch.int64, device=dev)
             self._fill_in = [plan.n_owned[q] + 1 for q in range(W)]
             self._fill_out = [plan.n_owned[me] + 1] * W
             self._n_fill = plan.nb + W

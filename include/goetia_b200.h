@@ -267,6 +267,14 @@ int gt_peer_close(void* ptr);
  * posted to the producer's overflow list in the owner's inbox as a full (table, slot) record and
  * applied there, so correctness does not depend on bucket capacities here either. */
 uint64_t gt_storage_inbox_bytes(const gt_storage* st, int rank);
+/* The same layout as host arithmetic (no GPU needed): region_entries[world] = R_q, in_region[n_buckets] =
+ * entry offset of bucket b inside a region of its owner, ovf_offset_bytes[world] = where the overflow lists
+ * start in rank q's inbox, inbox_bytes[world].  Rank p's entries for bucket b (owner q) land at entry
+ * p * R_q + in_region[b] of q's inbox; its overflow list at ovf_offset_bytes[q] + p * GT_OVF_RECORDS * 8.
+ * Returns the number of buckets. */
+int gt_shard_peer_layout(int kind, const uint64_t* tablesizes, int n_tables, int world,
+                         uint64_t budget_kmers, int slice_log2_bytes, uint64_t* region_entries,
+                         uint64_t* in_region, uint64_t* ovf_offset_bytes, uint64_t* inbox_bytes);
 /* inbox_of_rank[world]: device pointers valid in THIS process (entry `rank` = this rank's own
  * inbox of gt_storage_inbox_bytes bytes from gt_peer_alloc, the others from gt_peer_open).
  * fill_send [n_buckets + world]: bucket cursors, then the overflow-list cursors per owner rank;

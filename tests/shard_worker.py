@@ -3,6 +3,8 @@
     python tests/shard_worker.py cpu  KIND   -- gloo; the two kernels are emulated with numpy on top of the oracle's
                                                 hashes, so what is tested is the plan, the buffer layout and the
                                                 all-to-all bookkeeping of goetia_b200/shard.py (no GPU needed)
+    python tests/shard_worker.py cpu_p2p KIND -- gloo; the same for the peer transport's inbox layout, fill exchange and
+                                                overflow lists (gt_shard_peer_layout, ShardPlan.fill_perm)
     python tests/shard_worker.py cuda KIND   -- nccl; the real library on one GPU per rank
 
 Rank 0 gathers every rank's table parts, concatenates them in rank order and compares them byte
@@ -100,6 +102,77 @@ def main():
                     if ent.size:
                         np_apply(kind, slab, int(plan.slot0[b]) - lo + ent)
             parts.append(slab)
+    elif mode == "cpu_p2p":
+        # The peer transport's layout (gt_shard_peer_layout, the arithmetic gt_storage_attach_peers uses) and fill
+        # bookkeeping (ShardPlan.fill_perm), with the NVLink stores emulated by an all-to-all of the regions: rank p
+        # writes region p of every owner's inbox; every 17th update of a foreign bucket takes the overflow-list route.
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        plan = ShardPlan(kind, sizes, world, budget, slice_log2)
+        lay, perm = plan.peer_layout(), plan.fill_perm()
+        R, in_region = lay["region"], lay["in_region"]
+        assert all(int(lay["ovf_offset_bytes"][q]) >= world * int(R[q]) * 4 and int(lay["ovf_offset_bytes"][q]) % 16 == 0
+                   for q in range(world))
+        first = [int(np.nonzero(plan.table == t)[0][0]) for t in range(len(sizes))]
+        regions = [np.zeros(int(R[q]), dtype=np.int32) for q in range(world)]  # what I store into q's inbox
+        ovf = [[] for _ in range(world)]
+        fill = np.zeros(plan.nb + world, dtype=np.int64)
+        seen = 0
+        for r in range(my_o.size - 1):
+            seq = my_b[int(my_o[r]):int(my_o[r + 1])].tobytes()
+            fw, rc = Port.hash_sequence(1, K, seq)
+            h = np.minimum(fw, rc)
+            for t, size in enumerate(sizes):
+                bins = h % np.uint64(size)
+                for bn in bins:
+                    b = first[t] + (int(bn) >> plan.shift)
+                    q = int(plan.owner[b])
+                    seen += 1
+                    if q != rank and seen % 17 == 0:
+                        ovf[q].append((t << 59) | int(bn))
+                        fill[plan.nb + q] += 1
+                        continue
+                    assert fill[b] < plan.cap[b]
+                    regions[q][int(in_region[b]) + int(fill[b])] = int(bn) & ((1 << plan.shift) - 1)
+                    fill[b] += 1
+        # "stores": region `rank` of every inbox
+        inbox = torch.zeros(world * int(R[rank]), dtype=torch.int32)
+        dist.all_to_all_single(inbox, torch.from_numpy(np.concatenate(regions)), [int(R[rank])] * world, [int(R[q]) for q in range(world)])
+        n_own = plan.n_owned[rank]
+        fill_recv = torch.zeros(world * (n_own + 1), dtype=torch.int64)
+        dist.all_to_all_single(fill_recv, torch.from_numpy(fill[perm]), [n_own + 1] * world, [plan.n_owned[q] + 1 for q in range(world)])
+        fill_recv = fill_recv.numpy().reshape(world, n_own + 1)
+        cap_rec = max(1, max(len(o) for o in ovf))
+        cap_t = torch.tensor([cap_rec])
+        dist.all_reduce(cap_t, op=dist.ReduceOp.MAX)
+        cap_rec = int(cap_t.item())
+        lists_out = np.zeros((world, cap_rec), dtype=np.int64)
+        for q in range(world):
+            lists_out[q, :len(ovf[q])] = np.array(ovf[q], dtype=np.uint64).view(np.int64) if ovf[q] else []
+        lists_in = torch.zeros(world * cap_rec, dtype=torch.int64)
+        dist.all_to_all_single(lists_in, torch.from_numpy(lists_out.reshape(-1)))
+        lists_in = lists_in.numpy().view(np.uint64).reshape(world, cap_rec)
+        inbox = inbox.numpy()
+        parts = []
+        for t, size in enumerate(sizes):
+            lo, hi = int(plan.own_lo[rank, t]), int(plan.own_hi[rank, t])
+            slab = np.zeros(part_bytes(kind, lo, hi, hi == size), dtype=np.uint8)
+            for j, b in enumerate(plan.owned[rank]):
+                if plan.table[b] != t:
+                    continue
+                for p in range(world):
+                    n = int(fill_recv[p, j])
+                    o = p * int(R[rank]) + int(in_region[b])
+                    ent = inbox[o:o + n].astype(np.int64)
+                    if ent.size:
+                        np_apply(kind, slab, int(plan.slot0[b]) - lo + ent)
+            for p in range(world):
+                recs = lists_in[p, :int(fill_recv[p, n_own])]
+                mine = recs[(recs >> np.uint64(59)) == np.uint64(t)] & np.uint64((1 << 59) - 1)
+                if mine.size:
+                    assert int(mine.min()) >= lo and int(mine.max()) < hi
+                    for v in mine.astype(np.int64):  # one at a time: repeated slots must count every time
+                        np_apply(kind, slab, np.array([v - lo], dtype=np.int64))
+            parts.append(slab)
     else:
         import goetia_b200 as gb
         from goetia_b200 import _capi
@@ -146,7 +219,7 @@ def main():
     dist.gather_object([p.tobytes() for p in parts], gathered if rank == 0 else None, dst=0)
     if rank == 0:
         ref = Port(kind, 1, K, sizes)
-        passes = 1 if mode == "cpu" else int(os.environ.get("SHARD_ROUNDS", "2"))
+        passes = 1 if mode.startswith("cpu") else int(os.environ.get("SHARD_ROUNDS", "2"))
         for _ in range(passes):
             ref.insert_reads(bases, offsets)
         for t, want in enumerate(ref.tables()):

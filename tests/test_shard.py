@@ -83,6 +83,15 @@ def test_exchange_layout_gloo(kind, world):
     assert "tables bit-exact" in outs[0]
 
 
+@pytest.mark.parametrize("kind", [0, 1, 2])
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_layout_gloo(kind, world):
+    """The peer transport's inbox layout, fill exchange and overflow lists on CPU (stores emulated by all-to-all)."""
+    rcs, outs = launch("cpu_p2p", kind, world)
+    assert rcs == [0] * world, "\n".join(outs)
+    assert "tables bit-exact" in outs[0]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("transport", ["p2p", "nccl"])
 @pytest.mark.parametrize("kind", [0, 1, 2])
