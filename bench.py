@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- k-mers inserted per second on the BASELINE.json workload (one JSON line).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c3|c1|c2|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c3|c1|c2|c4|c5|storage]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one pass of the hot path (2-bit pack -> canonical rolling hash -> insert into the
@@ -63,7 +63,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["storage"])
     ap.add_argument("--reads", type=int, default=0, help="override the workload's read count (smoke runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -205,6 +205,8 @@ def cpu_reference_rate(kind, K, sizes, bases, offsets, budget_s, threads):
 
 def main():
     args = parse_args()
+    if args.workload == "storage":
+        return storage_arm(args)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -684,6 +686,52 @@ def sketch_arm(args, rank, world, local_rank, torch, gb, _capi):
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+    return 0
+
+
+def storage_arm(args):
+    """`--workload storage`: the reference's own storage micro-benchmark shape (src/goetia/benchmarks/
+    bench_storage.cc:17-61: n uniform 64-bit hashes, Storage(n/4, 4)) through the hash-vector entry points
+    gt_insert_hashes / gt_query_hashes with HOST buffers -- the only shape BASELINE.md holds published numbers
+    for (notebooks/Benchmarks.ipynb:336-342, hardware unknown).  Secondary benchmark, one GPU."""
+    import goetia_b200 as gb
+    from goetia_b200 import _capi
+    gb.init(int(os.environ.get("LOCAL_RANK", "0")))
+    L = _capi.lib()
+    n = args.reads or 100_000_000
+    published = {0: ("BitStorage", 1e8 / 13.42, 1e8 / 8.09), 1: ("ByteStorage", 1e8 / 17.75, 1e8 / 12.06),
+                 2: ("NibbleStorage", 1e8 / 35.79, 1e8 / 12.05)}
+    rng = np.random.default_rng(5)
+    hashes = rng.integers(0, 2**63, n, dtype=np.int64).view(np.uint64) * np.uint64(2) + rng.integers(0, 2, n).astype(np.uint64)
+    counts = np.zeros(n, dtype=np.int16)
+    rows = {}
+    for kind, (name, pub_ins, pub_q) in published.items():
+        st = [gb.BitStorage, gb.ByteStorage, gb.NibbleStorage][kind](gb.get_n_primes_near_x(4, n // 4))
+        t_ins, t_q = [], []
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            _capi.check(L.gt_insert_hashes(st.handle, hashes.ctypes.data, n, gb.MODE_BLIND, None), "gt_insert_hashes")
+            L.gt_synchronize()
+            t1 = time.perf_counter()
+            _capi.check(L.gt_query_hashes(st.handle, hashes.ctypes.data, n, counts.ctypes.data), "gt_query_hashes")
+            t2 = time.perf_counter()
+            if i >= args.warmup:
+                t_ins.append(t1 - t0)
+                t_q.append(t2 - t1)
+        assert int(counts.min()) >= 1
+        rows[name] = {"insert_hashes_per_s": n / float(np.median(t_ins)), "query_hashes_per_s": n / float(np.median(t_q)),
+                      "published_insert_hashes_per_s": pub_ins, "published_query_hashes_per_s": pub_q,
+                      "insert_vs_published": n / float(np.median(t_ins)) / pub_ins,
+                      "query_vs_published": n / float(np.median(t_q)) / pub_q}
+        st.close()
+    v = rows["BitStorage"]["insert_hashes_per_s"]
+    print(json.dumps({"metric": "hashes inserted/sec (host buffers, wall clock)", "value": v, "unit": "hashes/s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": n / v * 1e3, "higher_is_better": True,
+                      "scaling": "strong", "vs_baseline": rows["BitStorage"]["insert_vs_published"], "dtype": "u64",
+                      "data": "synthetic", "config": {"workload": "bench_storage.cc shape: %d uniform u64 hashes, Storage(n/4, 4), "
+                                                                  "gt_insert_hashes / gt_query_hashes from pageable host memory" % n,
+                                                      "published": "notebooks/Benchmarks.ipynb:336-342 (hardware unknown, 1 thread)"},
+                      "storages": rows}))
     return 0
 
 
