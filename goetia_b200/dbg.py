@@ -77,6 +77,25 @@ class dBG:
     def get_hasher(self):
         return type(self.hasher)(self.K)
 
+    # the graph IS-A shifter in the reference (dbg.hh:39-41 derives from ShifterType): the cursor members of
+    # hashshifter.hh:74-199 are reachable on it, and pythonize_dbg.py:50 exposes the cursor's hash as get_hash()
+    def hash_base(self, kmer):
+        return self.hasher.hash_base(kmer)
+
+    set_cursor = hash_base
+
+    def shift_right(self, out, inc):
+        return self.hasher.shift_right(out, inc)
+
+    def shift_left(self, inc, out):
+        return self.hasher.shift_left(inc, out)
+
+    def get_hash(self):
+        return self.hasher.get()
+
+    def is_initialized(self):
+        return self.hasher.is_initialized()
+
     def _value(self, item):
         if isinstance(item, (str, bytes)):
             return self.hash(item).value()

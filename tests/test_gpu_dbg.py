@@ -160,6 +160,11 @@ def test_single_kmer_semantics(gb, kind, _n, K):
         assert g.insert_and_query(kmer) == 1
         assert g.insert_and_query(g.hash(kmer)) == (2 if counting else 1)
     assert g.hash("A" * K) == g.hash("A" * K + "TTTT")  # tests/test_dbg.py:125-128
+    # the graph is a shifter too: cursor members and pythonize_dbg.py's get_hash
+    assert not g.is_initialized()
+    assert g.set_cursor(kmers[0]) == g.hash(kmers[0]) == g.get_hash()
+    assert g.shift_right(seq[0], seq[K]) == g.hash(kmers[1]) == g.get_hash()
+    assert g.shift_left(seq[0], seq[K]) == g.hash(kmers[0])
     with pytest.raises(Exception):
         g.insert_sequence("A" * (K - 1))  # tests/test_dbg.py:222-227
     c = g.clone()

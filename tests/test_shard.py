@@ -75,6 +75,27 @@ def test_plan_partitions_every_table():
             assert np.all(plan.cap >= 1_000_000 * plan.slots / np.asarray(sizes, dtype=np.float64)[plan.table])
 
 
+def test_plan_of_the_headline_workload():
+    """C3 (BitStorage, 4 x 8e9 bits) at 1 / 2 / 4 / 8 ranks: the bucket count stays at 120 (k_bucket's sweet spot),
+    every rank gets at least 3 slices of every table, the heaviest rank holds at most 4/30 of a table, and the peer
+    layout's inboxes hold `world` regions plus the overflow lists."""
+    from goetia_b200.shard import ShardPlan
+    from oracle.binding import Port
+    sizes = Port.primes_near(4, int(8e9))
+    for world in (1, 2, 4, 8):
+        plan = ShardPlan(0, sizes, world, 900_000_000 // max(1, world // 2), 0)
+        assert plan.nb == 120 and plan.shift == 28
+        for t, size in enumerate(sizes):
+            per_rank = [(plan.owner[plan.table == t] == r).sum() for r in range(world)]
+            assert min(per_rank) >= 2 and max(per_rank) <= -(-30 // world)
+            assert sum(int(plan.own_hi[r, t] - plan.own_lo[r, t]) for r in range(world)) == size
+        lay = plan.peer_layout()
+        for q in range(world):
+            assert int(lay["region"][q]) == int(plan.cap[plan.owned[q]].sum())
+            assert int(lay["inbox_bytes"][q]) >= world * int(lay["region"][q]) * 4
+        assert sorted(plan.fill_perm().tolist()) == list(range(plan.nb + world))
+
+
 @pytest.mark.parametrize("kind", [0, 1, 2])
 @pytest.mark.parametrize("world", [2, 3])
 def test_exchange_layout_gloo(kind, world):
