@@ -126,3 +126,85 @@ class FastxParser:
             self.close()
         except Exception:
             pass
+
+
+def _split_on_first(name, delims=" \t"):
+    """split_on_first, parsing.cc:31-54, statement for statement (including its quirk: a delimiter at index 0
+    leaves `left` empty and the scan goes on to the next one)."""
+    left = right = ""
+    for i, c in enumerate(name):
+        if left == "":
+            if c in delims:
+                left = name[:i]
+        elif c not in delims:
+            right = name[i:]
+            break
+    if left == "":
+        left = name
+    return left, right
+
+
+def check_is_pair(left, right):
+    """parsing.cc:56-86: do two record names belong to one read pair (/1 /2, or Illumina '1:' '2:' comments)?"""
+    lf, ls = _split_on_first(left)
+    rf, rs = _split_on_first(right)
+    if lf.endswith("/1") and rf.endswith("/2"):
+        return _split_on_first(lf, "/")[0] != "" and _split_on_first(lf, "/")[0] == _split_on_first(rf, "/")[0]
+    if lf == rf and ls.endswith("1:") and rs.endswith("2:"):
+        return True
+    if lf == rf and ls.endswith("/1") and rs.endswith("/2"):
+        return _split_on_first(ls, "/")[0] != "" and _split_on_first(ls, "/")[0] == _split_on_first(rs, "/")[0]
+    return False
+
+
+class SplitPairedReader:
+    """SplitPairedReader<FastxParser<DNA_SIMPLE>> (parsing/readers.hh:234-340): two files read in lock step."""
+
+    def __init__(self, left, right, strict=False, min_length=0, force_name_match=False):
+        self.left_parser = FastxParser(left, strict, min_length)
+        self.right_parser = FastxParser(right, strict, min_length)
+        self._strict, self._force_name_match, self._n_skipped = bool(strict), bool(force_name_match), 0
+
+    @classmethod
+    def build(cls, left, right, strict=False, min_length=0, force_name_match=False):
+        return cls(left, right, strict, min_length, force_name_match)
+
+    def is_complete(self):
+        if self.left_parser.is_complete() != self.right_parser.is_complete():
+            raise GoetiaB200Error("Mismatched split paired files.")
+        return self.left_parser.is_complete()
+
+    def next(self):
+        """RecordPair: (left or None, right or None)."""
+        if self.is_complete():
+            raise NoMoreReadsAvailable("NoMoreReadsAvailable")
+        pair, errs = [], []
+        for p in (self.left_parser, self.right_parser):
+            try:
+                pair.append(p.next())
+                errs.append(None)
+            except (InvalidCharacterException, InvalidRead) as e:
+                pair.append(None)
+                errs.append(e)
+        if self._strict:
+            for e in errs:
+                if e is not None:
+                    raise e
+        left, right = pair
+        if self._force_name_match and left is not None and right is not None and not check_is_pair(left.name, right.name):
+            if self._strict:
+                raise GoetiaB200Error("Unpaired reads")
+            self._n_skipped += 2
+            return None, None
+        return left, right
+
+    def __iter__(self):
+        while not self.is_complete():
+            yield self.next()
+
+    def n_skipped(self):
+        return self._n_skipped + self.left_parser.n_skipped() + self.right_parser.n_skipped()
+
+    def close(self):
+        self.left_parser.close()
+        self.right_parser.close()

@@ -142,3 +142,27 @@ def test_insert_fastx_matches_oracle(tmp_path, gb):
         for a, b in zip(g.get_raw(), ref.tables()):
             assert np.array_equal(a, b)
         ref.close()
+
+
+def test_split_paired_reader(tmp_path):
+    """SplitPairedReader (readers.hh:234-340; reference tests/test_parsing.py:68-80): lock-step pairs, skipped mates
+    come back as None, unequal files raise, force_name_match drops pairs whose names do not match."""
+    from goetia_b200 import parsing
+    d = str(tmp_path)
+    L = ["@p%d/1\n%s\n+\n%s\n" % (i, "ACGT" * 5 if i != 2 else "ACGN" * 5, "I" * 20) for i in range(5)]
+    R = ["@p%d/2\n%s\n+\n%s\n" % (i if i != 3 else 9, "TTGCA" * 4, "I" * 20) for i in range(5)]
+    open(d + "/l.fq", "w").write("".join(L))
+    open(d + "/r.fq", "w").write("".join(R))
+    pairs = list(parsing.SplitPairedReader.build(d + "/l.fq", d + "/r.fq"))
+    got = [(a.name if a else None, b.name if b else None) for a, b in pairs if a or b]
+    assert got == [("p0/1", "p0/2"), ("p1/1", "p1/2"), (None, "p2/2"), ("p3/1", "p9/2"), ("p4/1", "p4/2")]
+    rd = parsing.SplitPairedReader(d + "/l.fq", d + "/r.fq", force_name_match=True)
+    kept = [(a.name, b.name) for a, b in rd if a and b]
+    assert kept == [("p0/1", "p0/2"), ("p1/1", "p1/2"), ("p4/1", "p4/2")]
+    assert rd.n_skipped() == 2 + 1  # the unmatched pair, and the mate with the N
+    assert parsing.check_is_pair("r1 1:N:0:1", "r1 2:N:0:1") is False  # kseq names stop at the first blank
+    assert parsing.check_is_pair("r/1", "r/2") and not parsing.check_is_pair("/1", "/2")
+    open(d + "/short.fq", "w").write("".join(R[:3]))
+    bad = parsing.SplitPairedReader(d + "/l.fq", d + "/short.fq")
+    with pytest.raises(parsing.GoetiaB200Error):
+        list(bad)
