@@ -12,7 +12,7 @@ from .hashing import FwdLemireShifter, CanLemireShifter, Hash, Canonical  # noqa
 from .storage import BitStorage, ByteStorage, NibbleStorage, get_n_primes_near_x  # noqa: F401
 from .dbg import dBG  # noqa: F401
 from .sketch import SourmashSketch  # noqa: F401
-from .parsing import FastxParser, Record  # noqa: F401
+from .parsing import FastxParser, Record, SplitPairedReader  # noqa: F401
 from .filters import DiginormFilter, FilterProcessor, StreamingSolidFilter  # noqa: F401
 
 __version__ = "0.1.0"
