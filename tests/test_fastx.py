@@ -166,3 +166,59 @@ def test_split_paired_reader(tmp_path):
     bad = parsing.SplitPairedReader(d + "/l.fq", d + "/short.fq")
     with pytest.raises(parsing.GoetiaB200Error):
         list(bad)
+
+
+def _ref_or_skip():
+    from oracle import binding
+    if not binding.have_ref():
+        pytest.skip("oracle/_ref (the compiled reference) is not built here")
+    return binding.Ref
+
+
+def test_parser_fuzz_against_live_reference(tmp_path, engine, monkeypatch):
+    """Random FASTA / FASTQ-like text -- stray '@' '+' '>' at line starts, blank lines, CR LF, tabs, lower case,
+    foreign symbols, truncated tails -- through the product parser and through the compiled reference parser:
+    same kept sequences, same n_skipped, same error-or-not.  (Runs where oracle/_ref exists.)"""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    from goetia_b200 import parsing
+    Ref = _ref_or_skip()
+    fn = os.path.join(str(tmp_path), "fuzz.fx")
+    if engine == "parallel":
+        monkeypatch.setenv("GT_FASTX_CHUNK_BYTES", "64")  # several speculative chunks even in these tiny files
+
+    line = st.text(alphabet="ACGTacgtN@+> \t", min_size=0, max_size=12)
+    seqline = st.text(alphabet="ACGTacgtn", min_size=0, max_size=30)
+    rec_fa = st.tuples(st.just(">"), line, st.lists(seqline, min_size=0, max_size=3))
+    rec_fq = st.tuples(st.just("@"), line, st.lists(seqline, min_size=1, max_size=2), st.text(alphabet="I#@+>5", min_size=0, max_size=40))
+
+    def render(recs, eol, tail):
+        out = []
+        for r in recs:
+            if r[0] == ">":
+                out.append(">" + r[1] + eol + "".join(s + eol for s in r[2]))
+            else:
+                seq = "".join(r[2])
+                qual = (r[3] * 40)[:len(seq)] if len(r[3]) % 3 else r[3]  # mostly matching lengths, sometimes not
+                out.append("@" + r[1] + eol + "".join(s + eol for s in r[2]) + "+" + eol + qual + eol)
+        text = "".join(out)
+        return text[:len(text) - tail] if tail else text
+
+    @settings(max_examples=200, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.lists(st.one_of(rec_fa, rec_fq), min_size=0, max_size=8), st.sampled_from(["\n", "\r\n"]),
+           st.integers(0, 5), st.integers(0, 12))
+    def run(recs, eol, tail, min_length):
+        with open(fn, "w", newline="") as f:
+            f.write(render(recs, eol, tail))
+        try:
+            bb, oo, sk = Ref.parse_file(fn, strict=False, min_length=min_length)
+            want = ([bb[int(oo[i]):int(oo[i + 1])].tobytes() for i in range(oo.size - 1)], sk)
+        except ValueError:
+            want = None
+        try:
+            seqs, stats = parse_all(fn, False, min_length, max_bases=1 << 12)
+            got = (seqs, stats[1])
+        except parsing.InvalidRead:
+            got = None
+        assert got == want
+
+    run()
