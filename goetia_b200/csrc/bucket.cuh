@@ -30,7 +30,7 @@ namespace gt {
 
 constexpr int BK_MAX_BUCKETS = 1024;  // all tables together (3 x 4 KB of shared memory)
 constexpr int AP_THREADS = 256;
-constexpr int AP_PER_THREAD = 16;
+constexpr int AP_PER_THREAD = 32;
 constexpr int AP_CHUNK = AP_THREADS * AP_PER_THREAD;  // entries per apply CTA
 
 // What k_bucket needs: where each bucket's entries go.  With one GPU every bucket lives in the
@@ -58,10 +58,10 @@ struct ProducePlan {
     unsigned long long* n_dropped;    // overflowed updates of foreign slots that found the overflow list full too (an error)
     // Sharded storages, peer transport: an update that overflows the bucket of a slice held by rank q is
     // posted as a full (table, slot) record to this rank's overflow list in q's inbox (rare path).
-    // Counting storages: an update that overflows the bucket of a slice held HERE is not applied by k_bucket
-    // itself (a saturating CAS must not run beside the optimistic k_apply_add of the other store, see K2 for
-    // the counting storages); it is parked in the store's spill list and applied after that store's buckets.
-    unsigned long long* own_spill;    // [own_spill_cap] (table, slot) records; NULL for BitStorage
+    // An update that overflows the bucket of a slice held HERE is not applied by k_bucket itself (the apply of the
+    // other store may be merging windows into the tables with plain read-modify-writes, see K2w); it is parked
+    // in the store's spill list and applied after that store's windows.
+    unsigned long long* own_spill;    // [own_spill_cap] (table, slot) records
     uint32_t* own_spill_fill;
     uint32_t own_spill_cap;
     const uint8_t* bowner;            // [n_buckets] owner rank of each bucket (NULL: no overflow lists)
@@ -128,30 +128,28 @@ constexpr int BK_SUB = 8;  // positions per thread and sub-step
 constexpr int BK_OWN = BK_MAX_BUCKETS / TILE_THREADS;  // buckets a lane may own (4)
 constexpr uint32_t BK_NONE = 0xFFFFFFFFu;
 
-// an update of a slot held here whose bucket is full: BitStorage applies it on the spot (OR commutes with
-// everything); the counting storages park it (see ProducePlan::own_spill)
+// an update of a slot held here whose bucket is full is parked in the store's spill list (ProducePlan::own_spill):
+// k_bucket never writes a table itself, because the apply of the OTHER store may be merging windows into it
+// (a plain read-modify-write, see K2w) at the same time
 template <int KIND>
 __device__ __forceinline__ void apply_own_overflow(const TableSet& ts, const ProducePlan& bp, int t, uint64_t bin,
                                                    unsigned long long& direct, unsigned long long& dropped) {
-    if constexpr (KIND == 0) {
-        slot_insert<0, false>(ts.ptr[t], bin);
+    const uint32_t k = atomicAdd(bp.own_spill_fill, 1u);
+    if (k < bp.own_spill_cap) {
+        bp.own_spill[k] = ovf_pack(t, bin);
         ++direct;
     } else {
-        const uint32_t k = atomicAdd(bp.own_spill_fill, 1u);
-        if (k < bp.own_spill_cap) {
-            bp.own_spill[k] = ovf_pack(t, bin);
-            ++direct;
-        } else {
-            ++dropped;
-        }
+        ++dropped;
     }
 }
 
 template <int KIND>
 __device__ __forceinline__ void bucket_spill(const TableSet& ts, const ProducePlan& bp, int t, uint32_t b, uint32_t off,
                                              unsigned long long& direct, unsigned long long& dropped) {
-    // slow path: a 16 B group holding this one entry, or -- bucket full -- the table itself
-    const uint32_t g = atomicAdd(bp.bfill + b, 4u), cap = __ldg(bp.bcap + b);
+    // slow path: a 16 B group holding this one entry, or -- bucket full -- the overflow route.  The cursor is only
+    // bumped while it is below the capacity, so that skewed input (every update spilling) cannot wrap it.
+    const uint32_t cap = __ldg(bp.bcap + b);
+    const uint32_t g = __ldcg(bp.bfill + b) < cap ? atomicAdd(bp.bfill + b, 4u) : cap;
     if (g < cap) {
         *reinterpret_cast<uint4*>(bp.bptr[b] + g) = make_uint4(off, BK_PAD, BK_PAD, BK_PAD);
         return;
@@ -164,8 +162,37 @@ __device__ __forceinline__ void bucket_spill(const TableSet& ts, const ProducePl
     }
 }
 
-template <int KIND, bool CAN, int NT>
-__global__ void __launch_bounds__(TILE_THREADS, 4)  // <= 64 registers: leaves room for two k_apply CTAs per SM beside three of these
+// Bulk (TMA) copy of a staging row to its bucket: shared::cta -> global, 16-byte granules, tracked by the
+// issuing thread's bulk async-group.  The destination may be peer memory (NVLink) in a sharded storage.
+__device__ __forceinline__ void bulk_row_out(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// generic-proxy writes to shared memory (the appends) must be made visible to the async proxy that reads the rows
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// BIG: every table has >= 2^32 slots (rs == 0), so the reducer is the straight 32-bit-reciprocal one with no
+// run-time case analysis (the common case for tables larger than L2: C3's 8e9-bit tables).
+template <bool BIG>
+__device__ __forceinline__ uint64_t bin_of_t(uint64_t h, const TableSet& ts, const ProducePlan& bp, int t) {
+    if constexpr (BIG) {
+        const uint64_t d = bp.dsh[t];  // == ts.size[t]
+        const uint32_t m = bp.m32[t];
+        const uint32_t q = (uint32_t)(((uint64_t)(uint32_t)(h >> 32) * m + __umulhi((uint32_t)h, m)) >> 32);
+        const uint64_t ql = (uint64_t)q * (uint32_t)d;
+        const uint32_t qh = (uint32_t)(ql >> 32) + q * (uint32_t)(d >> 32);
+        const uint64_t r = h - (((uint64_t)qh << 32) | (uint32_t)ql);  // < 2 d
+        const uint64_t r2 = r - d;
+        return (int64_t)r2 < 0 ? r : r2;  // d <= 2^63 and r < 2 d: r - d is "negative" exactly when r < d
+    } else {
+        return bin_of(h, ts.size[t], ts.magic[t], bp.dsh[t], bp.m32[t], bp.rs[t]);
+    }
+}
+
+template <int KIND, bool CAN, int NT, bool BIG>
+__global__ void __launch_bounds__(TILE_THREADS, 4)  // <= 64 registers: three CTAs per SM and room for apply CTAs beside them
 k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts, const __grid_constant__ ProducePlan bp) {
     extern __shared__ __align__(16) uint64_t smem[];
     const int K = a.K;
@@ -177,8 +204,9 @@ k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts
     ulonglong2* tab = reinterpret_cast<ulonglong2*>(smem);           // 8 x 16 B: per-base roll constants
     ulonglong2* tab2 = tab + 8;                                      // 16 x 16 B: per-base-pair seed constants {fw, rc}
     uint64_t* sw = smem + 48;                                        // packed tile + halo
-    uint32_t* stage = reinterpret_cast<uint32_t*>(sw + tile_words + (tile_words & 1));  // [nb][C]
-    uint32_t* cnt = stage + (size_t)nb * C;                          // [2][nb] appends of this / the next sub-step
+    uint32_t* stage = reinterpret_cast<uint32_t*>(sw + tile_words + (tile_words & 1));  // [nb][C], 16-byte aligned rows
+    // cnt[2][nb]: next free staging index of every bucket, ABSOLUTE (row b starts at b * C), for this / the next sub-step
+    uint32_t* cnt = stage + (size_t)nb * C;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 4) {
         tab[tid] = make_ulonglong2(lemire_T(tid), rotl64(lemire_T(3 - tid), (unsigned)K));
@@ -189,7 +217,7 @@ k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts
         const int c0 = tid & 3, c1 = tid >> 2;
         tab2[tid] = make_ulonglong2(rotl1(lemire_T(c0)) ^ lemire_T(c1), lemire_T(3 - c0) ^ rotl1(lemire_T(3 - c1)));
     }
-    for (int b = tid; b < 2 * nb; b += TILE_THREADS) cnt[b] = 0;
+    for (int b = tid; b < 2 * nb; b += TILE_THREADS) cnt[b] = (uint32_t)(b < nb ? b : b - nb) * C;
     const uint64_t n_tiles = (a.n_bases + TILE_POS - 1) / TILE_POS;
     const uint32_t slot_mask = (uint32_t)((1ull << bp.shift) - 1);
     unsigned long long direct = 0, dropped = 0;
@@ -291,91 +319,91 @@ k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts
                         const uint64_t h = CAN ? (fw < rc ? fw : rc) : fw;  // Canonical::value(), canonical.hh:124-126
 #pragma unroll
                         for (int t = 0; t < nt; ++t) {
-                            const uint64_t bin = bin_of(h, ts.size[t], ts.magic[t], bp.dsh[t], bp.m32[t], bp.rs[t]);
+                            const uint64_t bin = bin_of_t<BIG>(h, ts, bp, t);
                             const uint32_t b = bp.first[t] + (uint32_t)(bin >> bp.shift);
                             const uint32_t off = (uint32_t)bin & slot_mask;
-                            const uint32_t pos = atomicAdd(&cn[b], 1u);
-                            if (pos < C) stage[b * C + pos] = off;
+                            const uint32_t idx = atomicAdd(&cn[b], 1u);  // absolute staging index
+                            if (idx < b * C + C) stage[idx] = off;
                             else bucket_spill<KIND>(ts, bp, t, b, off, direct, dropped);
                         }
                     }
                 }
             }
+            fence_async_smem();
             __syncthreads();
-            // ---- copy the rows out.  Lane l of warp w owns buckets w + 8*l + 256*rr (rr < 4) and keeps
-            // their write position in registers: room in the global bucket is taken R entries at a
-            // time and the next piece is requested one flush ahead, so the latency of the global
-            // cursor atomic is hidden behind the next append phase (R == 0: exact-size requests).
+            // ---- copy the rows out.  Lane l of warp w owns buckets w + 8*l + 256*rr (rr < 4) and keeps their write
+            // position in registers: room in the global bucket is taken R entries at a time and the next piece is
+            // requested one flush ahead, so the latency of the global cursor atomic is hidden behind the next append
+            // phase (R == 0: exact-size requests).  The owner pads its row to a multiple of 16 bytes and sends it
+            // with ONE bulk copy (two when the run straddles a piece boundary); nobody else touches the row.
             uint32_t* cz = cnt + (phase ^ 1) * nb;
+            bool issued = false;
 #pragma unroll
             for (int rr = 0; rr < BK_OWN; ++rr) {
-                const int base = warp + rr * TILE_THREADS;
-                if (base >= nb) break;
-                const int mine = base + 8 * lane;  // TILE_THREADS / 32 == 8 warps
-                uint32_t n = 0, d0 = 0, l0 = 0, d1 = 0, l1 = 0;
-                if (mine < nb) {
-                    n = min(cn[mine], C);
-                    cz[mine] = 0;  // the other half is idle now: clear it for the next sub-step
-                    const uint32_t n4 = (n + 3u) & ~3u;
-                    if (R == 0) {
-                        if (n4) { d0 = atomicAdd(bp.bfill + mine, n4); l0 = n4; }
-                    } else if (n4) {
-                        l0 = min(c_left[rr], n4);
-                        d0 = c_pos[rr];
-                        c_pos[rr] += l0;
-                        c_left[rr] -= l0;
-                        l1 = n4 - l0;
-                        if (l1) {  // continue in the next piece (R >= the longest run)
-                            if (c_nxt[rr] == BK_NONE) c_nxt[rr] = atomicAdd(bp.bfill + mine, R);
-                            d1 = c_nxt[rr];
-                            c_nxt[rr] = BK_NONE;
-                            c_pos[rr] = d1 + l1;
-                            c_left[rr] = R - l1;
-                        }
-                        if (c_left[rr] < C4 && c_nxt[rr] == BK_NONE) c_nxt[rr] = atomicAdd(bp.bfill + mine, R);
+                const int mine = warp + rr * TILE_THREADS + 8 * lane;  // TILE_THREADS / 32 == 8 warps
+                if (mine >= nb) break;
+                const uint32_t row0 = (uint32_t)mine * C;
+                const uint32_t n = min(cn[mine] - row0, C);
+                cz[mine] = row0;  // the other half is idle now: rewind it for the next sub-step
+                if (n == 0) continue;
+                const uint32_t n4 = (n + 3u) & ~3u;
+                uint32_t* row = stage + row0;
+                for (uint32_t e = n; e < n4; ++e) row[e] = BK_PAD;
+                uint32_t d0 = 0, l0 = n4, d1 = 0, l1 = 0;
+                if (R == 0) {
+                    d0 = atomicAdd(bp.bfill + mine, n4);
+                } else {
+                    l0 = min(c_left[rr], n4);
+                    d0 = c_pos[rr];
+                    c_pos[rr] += l0;
+                    c_left[rr] -= l0;
+                    l1 = n4 - l0;
+                    if (l1) {  // continue in the next piece (R >= the longest run)
+                        if (c_nxt[rr] == BK_NONE) c_nxt[rr] = atomicAdd(bp.bfill + mine, R);
+                        d1 = c_nxt[rr];
+                        c_nxt[rr] = BK_NONE;
+                        c_pos[rr] = d1 + l1;
+                        c_left[rr] = R - l1;
                     }
+                    if (c_left[rr] < C4 && c_nxt[rr] == BK_NONE) c_nxt[rr] = atomicAdd(bp.bfill + mine, R);
                 }
-                const unsigned have = __ballot_sync(0xffffffffu, n != 0);
-                for (unsigned m = have; m; m &= m - 1) {
-                    const int l = __ffs(m) - 1;
-                    const uint32_t bn = __shfl_sync(0xffffffffu, n, l);
-                    const uint32_t bd0 = __shfl_sync(0xffffffffu, d0, l), bl0 = __shfl_sync(0xffffffffu, l0, l);
-                    const uint32_t bd1 = __shfl_sync(0xffffffffu, d1, l);
-                    const uint32_t b = (uint32_t)(base + 8 * l);
-                    const uint32_t cap = __ldg(bp.bcap + b);
-                    uint32_t* dst = bp.bptr[b];
-                    const uint32_t* row = stage + b * C;
-                    for (uint32_t e = 4 * lane; e < bn; e += 128) {
-                        uint4 v = *reinterpret_cast<const uint4*>(row + e);
-                        if (e + 1 >= bn) v.y = BK_PAD;
-                        if (e + 2 >= bn) v.z = BK_PAD;
-                        if (e + 3 >= bn) v.w = BK_PAD;
-                        const uint32_t at = e < bl0 ? bd0 + e : bd1 + (e - bl0);
+                const uint32_t cap = __ldg(bp.bcap + mine);
+                uint32_t* dst = bp.bptr[mine];
+                if ((l0 == 0 || d0 + l0 <= cap) && (l1 == 0 || d1 + l1 <= cap)) {
+                    fence_async_smem();  // the pad entries above
+                    if (l0) bulk_row_out(dst + d0, row, l0 * 4u);
+                    if (l1) bulk_row_out(dst + d1, row + l0, l1 * 4u);
+                    issued = true;
+                } else {  // bucket (nearly) full -- skewed input: group by group, the excess takes the overflow route
+                    int t = 0;
+                    while ((uint32_t)mine >= bp.first[t + 1]) ++t;
+                    for (uint32_t e = 0; e < n4; e += 4) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(row + e);
+                        const uint32_t at = e < l0 ? d0 + e : d1 + (e - l0);
                         if (at < cap) {
                             *reinterpret_cast<uint4*>(dst + at) = v;
-                        } else {  // bucket full (skewed input): apply here, correctness never depends on capacity
-                            int t = 0;
-                            while (b >= bp.first[t + 1]) ++t;
-                            const uint32_t offs[4] = {v.x, v.y, v.z, v.w};
+                            continue;
+                        }
+                        const uint32_t offs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                if (offs[k] == BK_PAD) continue;
-                                const uint64_t bin = ((uint64_t)(b - bp.first[t]) << bp.shift) + offs[k];
-                                if (bin >= bp.own_lo[t] && bin < bp.own_hi[t]) {
-                                    apply_own_overflow<KIND>(ts, bp, t, bin, direct, dropped);
-                                } else {
-                                    post_foreign(bp, t, b, bin, dropped);
-                                }
-                            }
+                        for (int k = 0; k < 4; ++k) {
+                            if (offs[k] == BK_PAD) continue;
+                            const uint64_t bin = ((uint64_t)((uint32_t)mine - bp.first[t]) << bp.shift) + offs[k];
+                            if (bin >= bp.own_lo[t] && bin < bp.own_hi[t]) apply_own_overflow<KIND>(ts, bp, t, bin, direct, dropped);
+                            else post_foreign(bp, t, (uint32_t)mine, bin, dropped);
                         }
                     }
                 }
+            }
+            if (issued) {
+                bulk_commit();
+                bulk_wait_read();  // the rows are appended to again after the barrier below
             }
             __syncthreads();
             phase ^= 1;
         }
     }
-    // what is left of the pieces this CTA took is filled with pad entries (k_apply skips them)
+    // what is left of the pieces this CTA took is filled with pad entries (the apply skips them)
     if (R) {
 #pragma unroll
         for (int rr = 0; rr < BK_OWN; ++rr) {
@@ -398,12 +426,11 @@ k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts
 // ------------------------------------------------------------------------------------------
 // chunk_start[n_buckets+1]: first CTA of each bucket, host-built from the capacities, so the
 // grid needs no device-side planning; CTAs past a bucket's fill exit at once.
-// only_failed != NULL: apply only the slices whose conservation check failed (replay pass of the counting
-// storages, see below); items_per_slice consecutive items belong to one slice.
+// The plain apply (global atomics): used when little is pending relative to the tables (store_apply_async).
 template <int KIND>
 __global__ void __launch_bounds__(AP_THREADS)
 k_apply(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ items, const uint32_t* __restrict__ chunk_start,
-        int n_items, const unsigned long long* __restrict__ only_failed = nullptr, int items_per_slice = 1) {
+        int n_items) {
     __shared__ uint32_t s_b;
     if (threadIdx.x == 0) {
         // item of this CTA: largest b with chunk_start[b] <= blockIdx.x
@@ -416,7 +443,6 @@ k_apply(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ items
     }
     __syncthreads();
     const uint32_t b = s_b;
-    if (only_failed && __ldcg(only_failed + b / (uint32_t)items_per_slice) == 0ull) return;
     const ApplyItem it = items[b];
     const uint32_t fill = min(__ldcg(it.fill), it.cap);
     const uint32_t e0 = (blockIdx.x - __ldg(chunk_start + b)) * (uint32_t)AP_CHUNK;
@@ -443,36 +469,6 @@ k_apply(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ items
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// K2 for the counting storages (ByteStorage / NibbleStorage).
-//
-// A saturating increment by CAS costs a load plus a compare-and-swap per update and runs at a fraction of the
-// fire-and-forget atomic rate (measured on B200: ~26 G updates/s against ~200 G RED/s; an atomicAdd that
-// returns its old value manages ~55 G/s).  But saturation is rare, and 32-bit word arithmetic is linear: as long
-// as no counter of a slice is hit while it stands at its maximum, a plain RED.ADD of 1 << shift IS the saturating
-// increment.  So a slice is applied optimistically and checked by a conservation law:
-//   k_slice_sums<-1>   delta[slice] -= sum of all counters of the slice          (before)
-//   k_apply_red        every update is one RED.ADD; delta[slice] -= updates applied
-//   k_slice_sums<+1>   delta[slice] += sum of all counters of the slice          (after)
-// An add that lands on a counter below its maximum raises the slice's counter sum by exactly 1; one that lands on
-// a counter AT its maximum wraps it (and carries into the neighbour, or off the word) and changes the sum by
-// <= 1 - max.  Hence delta[slice] == 0 <=> no add wrapped <=> the slice already holds min(max, hits).  For the
-// (rare) slices with delta != 0:
-//   k_apply_red<UNDO>  subtracts every update again -- exact whatever the wraps did to neighbouring counters,
-//                      because add and subtract cancel mod 2^32;
-//   k_apply(only_failed) replays the updates with the saturating CAS.
-// A slice that failed is remembered as hot and goes straight to the CAS replay in the following applies (4-bit
-// counters saturate routinely once a table fills up); every 8th apply clears the flags and tries again.
-// GT_APPLY_CAS=1 forces the plain CAS apply.
-// Nothing else writes the tables meanwhile: k_bucket parks its own overflow (ProducePlan::own_spill) and the direct
-// writers are ordered against the apply stream (direct_begin / direct_end).  Final bytes are bit-exact.
-// Items of one slice are consecutive (items_per_slice = ranks that produced for it): slice = item / items_per_slice.
-// ------------------------------------------------------------------------------------------
-struct SliceDesc {
-    uint64_t slot0, slots;
-    uint32_t table;
-};
-
 template <int KIND>
 __device__ __forceinline__ void counter_addr(uint32_t off, uint32_t& word, uint32_t& sh) {
     if constexpr (KIND == 1) {
@@ -484,94 +480,274 @@ __device__ __forceinline__ void counter_addr(uint32_t off, uint32_t& word, uint3
     }
 }
 
-// sum of the 4 byte counters / 8 nibble counters of a table word
+// ------------------------------------------------------------------------------------------
+// K2w: the apply through shared-memory WINDOWS (all three storages).
+//
+// k_apply above sends one L2 atomic per update.  That is a hard ceiling (measured on B200: ~200 G RED/s chip-wide,
+// and every RED of a warp is its own L1->L2 request, so the SM's load/store path is busy 32 cycles per warp
+// instruction -- which is also what slows k_bucket down when the two kernels share an SM), and for the counting
+// storages a saturating increment needs a CAS (load + compare-and-swap, ~26 G/s).  Shared-memory atomics are an
+// order of magnitude cheaper, so a slice is cut once more into WINDOWS of 2^wshift slots that fit shared memory:
+//
+//   k_rebucket   radix-partitions the entries of a slice (all sources) by window: per 8192-entry chunk a counting
+//                sort in shared memory, one global cursor reservation per (chunk, window), runs written out
+//                coalesced to the window's SUB-BUCKET (entries become window-local offsets);
+//   k_apply_win  one CTA per window: zero the window image in shared memory, stream the sub-bucket with 16 B loads
+//                and OR / saturating-add into shared memory, then merge the image into the table ONCE with 16 B
+//                loads and stores (table |= image; per-byte / per-nibble saturating add for the counting storages).
+//
+// The image of a counting window holds the hits of this apply per counter, saturating at the counter's maximum, so
+// table' = min(max, table + min(max, hits)) = min(max, table + hits): exactly the reference's one-at-a-time
+// saturating increments (bytestorage.cc:60-113, nibblestorage.cc:60-100) in any order.  Slices that are not larger
+// than a window skip k_rebucket (n_win == 1: the level-1 entries already are window-local).
+// The merge is a plain read-modify-write, so nothing else may write the tables while an apply runs: k_bucket
+// parks the updates that overflow a bucket of its own slots in the store's spill list (ProducePlan::own_spill,
+// applied after the store's windows), a sub-bucket that overflows applies the excess with global atomics from
+// k_rebucket (which runs before any window of that apply), and the direct writers (k_walk, k_insert_hashes) are
+// ordered against the apply stream (direct_begin / direct_end).
+// ------------------------------------------------------------------------------------------
+constexpr int RB_THREADS = 512;
+constexpr int RB_PER_THREAD = AP_CHUNK / RB_THREADS;  // 16
+constexpr int AW_THREADS = 512;
+constexpr int WIN_MAX_PER_SLICE = 1024;
+
+struct SliceWin {
+    uint32_t* sub;         // two-level: n_win sub-buckets of cap2 entries each (window-local offsets)
+    uint32_t* sub_fill;    // two-level: n_win cursors
+    uint64_t slot0;        // first slot of the slice in table coordinates
+    uint32_t cap2;
+    uint32_t n_win;        // windows of this slice that exist (the last slice of a table may be short)
+    uint32_t words;        // 32-bit table words of the slice that exist (multiple of 4)
+    uint32_t table;
+    uint32_t win0;         // id of the slice's first window among all windows applied here
+};
+
 template <int KIND>
-__device__ __forceinline__ uint32_t counter_sum(uint32_t x) {
-    if constexpr (KIND == 1) return __dp4a(x, 0x01010101u, 0u);
-    else return __dp4a(x & 0x0f0f0f0fu, 0x01010101u, __dp4a((x >> 4) & 0x0f0f0f0fu, 0x01010101u, 0u));
+__device__ __forceinline__ uint32_t* slice_words_ptr(const TableSet& ts, uint32_t table, uint64_t slot0) {
+    return ts.ptr[table] + (KIND == 0 ? (slot0 >> 5) : KIND == 1 ? (slot0 >> 2) : (slot0 >> 3));
 }
 
-// grid (x, n_slices): delta[slice] += SIGN * (sum of the counters of the slice)
-template <int KIND, int SIGN>
-__global__ void __launch_bounds__(256) k_slice_sums(const __grid_constant__ TableSet ts, const SliceDesc* __restrict__ slices,
-                                                     unsigned long long* __restrict__ delta) {
-    const SliceDesc sd = slices[blockIdx.y];
-    constexpr uint32_t spw = KIND == 1 ? 4u : 8u;
-    const uint32_t* tbl = ts.ptr[sd.table] + sd.slot0 / spw;  // slices start on a word boundary
-    const uint64_t n_words = (sd.slots + spw - 1) / spw;      // a table's last word may be partial: its padding is zero
-    unsigned long long mine = 0;
-    const uint4* v = reinterpret_cast<const uint4*>(tbl);
-    const uint64_t n4 = (reinterpret_cast<uintptr_t>(tbl) & 15) == 0 ? n_words / 4 : 0;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint4 x = __ldcg(v + i);
-        mine += counter_sum<KIND>(x.x) + counter_sum<KIND>(x.y) + counter_sum<KIND>(x.z) + counter_sum<KIND>(x.w);
-    }
-    for (uint64_t w = n4 * 4 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words; w += (uint64_t)gridDim.x * blockDim.x)
-        mine += counter_sum<KIND>(__ldcg(tbl + w));
-    for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
-    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(delta + blockIdx.y, SIGN > 0 ? mine : 0ull - mine);
-}
-
-// UNDO = false: the optimistic pass.  UNDO = true: subtract the same updates again, only in the slices whose
-// check failed (delta != 0 after k_slice_sums<+1>); delta is left untouched so that the replay sees it too.
-// hot[slice] != 0: the slice saturated in a recent apply; it is left to the CAS replay straight away (no adds,
-// nothing to undo) until the flags are cleared again (every 8th apply retries the optimistic path).
-template <int KIND, bool UNDO>
-__global__ void __launch_bounds__(AP_THREADS)
-k_apply_red(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ items, const uint32_t* __restrict__ chunk_start,
-            int n_items, int items_per_slice, unsigned long long* __restrict__ delta, const uint32_t* __restrict__ hot) {
-    static_assert(KIND == 1 || KIND == 2, "counting storages only");
-    __shared__ uint32_t s_b;
+__device__ __forceinline__ uint32_t item_of_chunk(const uint32_t* __restrict__ chunk_start, int n_items, uint32_t* s_b) {
     if (threadIdx.x == 0) {
         uint32_t lo = 0, hi = (uint32_t)n_items;
         while (hi - lo > 1) {
             uint32_t mid = (lo + hi) >> 1;
             if (__ldg(chunk_start + mid) <= blockIdx.x) lo = mid; else hi = mid;
         }
-        s_b = lo;
+        *s_b = lo;
     }
     __syncthreads();
-    const uint32_t b = s_b;
-    if (__ldcg(hot + b / (uint32_t)items_per_slice) != 0u) return;
-    if (UNDO && __ldcg(delta + b / (uint32_t)items_per_slice) == 0ull) return;
+    return *s_b;
+}
+
+// shared memory: sorted[AP_CHUNK] | hist[nw] | lbase[nw] | gdelta[nw] | warp_sums[16]
+template <int KIND>
+__global__ void __launch_bounds__(RB_THREADS)
+k_rebucket(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ items, const uint32_t* __restrict__ chunk_start,
+           int n_items, int items_per_slice, const SliceWin* __restrict__ slices, int wshift, int nw_max) {
+    extern __shared__ __align__(16) uint32_t rb_sm[];
+    __shared__ uint32_t s_b;
+    const uint32_t b = item_of_chunk(chunk_start, n_items, &s_b);
     const ApplyItem it = items[b];
     const uint32_t fill = min(__ldcg(it.fill), it.cap);
     const uint32_t e0 = (blockIdx.x - __ldg(chunk_start + b)) * (uint32_t)AP_CHUNK;
     if (e0 >= fill) return;
-    uint32_t* tbl = ts.ptr[it.table] + (KIND == 1 ? (it.slot0 >> 2) : (it.slot0 >> 3));
-    const uint32_t* src = it.src;
+    const SliceWin sl = slices[b / (uint32_t)items_per_slice];
+    const uint32_t nw = sl.n_win;
+    uint32_t* sorted = rb_sm;
+    uint32_t* hist = rb_sm + AP_CHUNK;
+    uint32_t* lbase = hist + nw_max;
+    uint32_t* gdelta = lbase + nw_max;
+    uint32_t* wsum = gdelta + nw_max;
+    const int tid = threadIdx.x;
+    for (uint32_t d = tid; d < nw; d += RB_THREADS) hist[d] = 0;
+    __syncthreads();
     const uint32_t n = min((uint32_t)AP_CHUNK, fill - e0);
-    uint32_t applied = 0;
-    auto one = [&](uint32_t off) {
-        if (off == BK_PAD) return;
-        uint32_t word, sh;
-        counter_addr<KIND>(off, word, sh);
-        atomicAdd(tbl + word, UNDO ? 0u - (1u << sh) : (1u << sh));  // result unused: RED.ADD
-        ++applied;
-    };
-    if (n == AP_CHUNK && ((reinterpret_cast<uintptr_t>(src + e0) & 15) == 0)) {
-        const uint4* v = reinterpret_cast<const uint4*>(src + e0);
+    const uint32_t* src = it.src + e0;
+    uint32_t v[RB_PER_THREAD], r[RB_PER_THREAD];
+    const bool vec = n == AP_CHUNK && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
 #pragma unroll
-        for (int k = 0; k < AP_PER_THREAD / 4; ++k) {
-            const uint4 x = __ldcs(v + k * AP_THREADS + threadIdx.x);
-            one(x.x); one(x.y); one(x.z); one(x.w);
+    for (int k = 0; k < RB_PER_THREAD / 4; ++k) {
+        if (vec) {
+            const uint4 x = __ldcs(reinterpret_cast<const uint4*>(src) + k * RB_THREADS + tid);
+            v[4 * k] = x.x; v[4 * k + 1] = x.y; v[4 * k + 2] = x.z; v[4 * k + 3] = x.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t e = (uint32_t)(k * 4 + j) * RB_THREADS + tid;
+                v[4 * k + j] = e < n ? __ldcs(src + e) : BK_PAD;
+            }
         }
-    } else {
-        for (uint32_t e = threadIdx.x; e < n; e += AP_THREADS) one(__ldcs(src + e0 + e));
     }
-    if (!UNDO) {
-        for (int o = 16; o; o >>= 1) applied += __shfl_down_sync(0xffffffffu, applied, o);
-        if ((threadIdx.x & 31) == 0 && applied) atomicAdd(delta + b / (uint32_t)items_per_slice, 0ull - (unsigned long long)applied);
+#pragma unroll
+    for (int k = 0; k < RB_PER_THREAD; ++k)
+        if (v[k] != BK_PAD) r[k] = atomicAdd(&hist[v[k] >> wshift], 1u);
+    __syncthreads();
+    // exclusive scan of hist over nw (<= 1024) windows: thread t owns windows 2t, 2t+1
+    uint32_t h0 = 0, h1 = 0;
+    if (2u * tid < nw) h0 = hist[2 * tid];
+    if (2u * tid + 1 < nw) h1 = hist[2 * tid + 1];
+    uint32_t incl = h0 + h1;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((tid & 31) >= o) incl += t;
+    }
+    if ((tid & 31) == 31) wsum[tid >> 5] = incl;
+    __syncthreads();
+    uint32_t run = incl - (h0 + h1);
+    for (int w = 0; w < (tid >> 5); ++w) run += wsum[w];
+    // one reservation per (chunk, window) that received entries
+    if (2u * tid < nw) {
+        lbase[2 * tid] = run;
+        gdelta[2 * tid] = h0 ? atomicAdd(sl.sub_fill + 2 * tid, h0) - run : 0u;
+    }
+    if (2u * tid + 1 < nw) {
+        lbase[2 * tid + 1] = run + h0;
+        gdelta[2 * tid + 1] = h1 ? atomicAdd(sl.sub_fill + 2 * tid + 1, h1) - (run + h0) : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RB_PER_THREAD; ++k)
+        if (v[k] != BK_PAD) sorted[lbase[v[k] >> wshift] + r[k]] = v[k];
+    __syncthreads();
+    // total valid entries = exclusive base of the last window + its count
+    const uint32_t total = lbase[nw - 1] + hist[nw - 1];
+    const uint32_t wmask = (1u << wshift) - 1u;
+    for (uint32_t j = tid; j < total; j += RB_THREADS) {
+        const uint32_t x = sorted[j];
+        const uint32_t d = x >> wshift;
+        const uint32_t pos = j + gdelta[d];
+        if (pos < sl.cap2) {
+            sl.sub[(size_t)d * sl.cap2 + pos] = x & wmask;
+        } else {  // sub-bucket full (skewed input): apply here; no window of this apply has started yet
+            slot_insert<KIND, false>(ts.ptr[sl.table], sl.slot0 + x);
+        }
     }
 }
 
-// after the undo pass: slices that failed the check become hot; hot slices (old and new) are what the replay applies
-__global__ void __launch_bounds__(256) k_mark_hot(unsigned long long* __restrict__ delta, uint32_t* __restrict__ hot, int n_slices) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_slices) return;
-    const uint32_t h = (hot[s] != 0u || delta[s] != 0ull) ? 1u : 0u;
-    hot[s] = h;
-    delta[s] = h;
+template <int KIND>
+__device__ __forceinline__ void window_update(uint32_t* __restrict__ win, uint32_t off) {
+    if constexpr (KIND == 0) {
+        atomicOr(win + (off >> 5), 1u << (off & 31));
+    } else {
+        uint32_t word, sh;
+        counter_addr<KIND>(off, word, sh);
+        constexpr uint32_t fmax = KIND == 1 ? 255u : 15u;
+        uint32_t old = win[word];
+        while (((old >> sh) & fmax) != fmax) {
+            const uint32_t prev = atomicCAS(win + word, old, old + (1u << sh));
+            if (prev == old) break;
+            old = prev;
+        }
+    }
+}
+
+template <int KIND>
+__device__ __forceinline__ uint32_t window_merge(uint32_t t, uint32_t d) {
+    if constexpr (KIND == 0) return t | d;
+    else if constexpr (KIND == 1) return __vaddus4(t, d);
+    else {
+        const uint32_t lo = __vminu4((t & 0x0f0f0f0fu) + (d & 0x0f0f0f0fu), 0x0f0f0f0fu);
+        const uint32_t hi = __vminu4(((t >> 4) & 0x0f0f0f0fu) + ((d >> 4) & 0x0f0f0f0fu), 0x0f0f0f0fu);
+        return lo | (hi << 4);
+    }
+}
+
+// One CTA per window.  TWO_LEVEL: the window's sub-bucket (k_rebucket's output); otherwise the slice is the window
+// and its sources are the level-1 items [slice * items_per_slice, +items_per_slice).
+template <int KIND, bool TWO_LEVEL>
+__global__ void __launch_bounds__(AW_THREADS)
+k_apply_win(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ items, int items_per_slice,
+            const SliceWin* __restrict__ slices, const uint32_t* __restrict__ win_slice, int wshift) {
+    extern __shared__ __align__(16) uint32_t win[];
+    const uint32_t s = __ldg(win_slice + blockIdx.x);
+    const SliceWin sl = slices[s];
+    const uint32_t d = blockIdx.x - sl.win0;
+    constexpr int spw_log2 = KIND == 0 ? 5 : KIND == 1 ? 2 : 3;
+    const uint32_t wwords = 1u << (wshift - spw_log2);  // words of a full window
+    const uint32_t w_lo = d * wwords;
+    if (w_lo >= sl.words) return;
+    const uint32_t nwords = min(wwords, sl.words - w_lo);  // multiple of 4
+    const int n_src = TWO_LEVEL ? 1 : items_per_slice;
+    uint32_t total = 0;
+    if constexpr (TWO_LEVEL) {
+        total = min(__ldcg(sl.sub_fill + d), sl.cap2);
+    } else {
+        for (int q = 0; q < n_src; ++q) {
+            const ApplyItem it = items[s * (uint32_t)items_per_slice + q];
+            total += min(__ldcg(it.fill), it.cap);
+        }
+    }
+    if (total == 0) return;  // nothing for this window: the table is not touched
+    const int tid = threadIdx.x;
+    uint4* win4 = reinterpret_cast<uint4*>(win);
+    for (uint32_t i = tid; i < nwords / 4; i += AW_THREADS) win4[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    for (int q = 0; q < n_src; ++q) {
+        const uint32_t* src;
+        uint32_t n;
+        if constexpr (TWO_LEVEL) {
+            src = sl.sub + (size_t)d * sl.cap2;
+            n = total;
+        } else {
+            const ApplyItem it = items[s * (uint32_t)items_per_slice + q];
+            src = it.src;
+            n = min(__ldcg(it.fill), it.cap);
+        }
+        // 16 B streaming loads over the aligned body, scalar head / tail
+        const uint32_t head = min(n, (uint32_t)((16 - (reinterpret_cast<uintptr_t>(src) & 15)) & 15) / 4);
+        if ((uint32_t)tid < head) {
+            const uint32_t x = __ldcs(src + tid);
+            if (x != BK_PAD) window_update<KIND>(win, x);
+        }
+        const uint32_t body = (n - head) / 4;
+        const uint4* v = reinterpret_cast<const uint4*>(src + head);
+        uint32_t i = tid;
+        for (; i + 3 * AW_THREADS < body; i += 4 * AW_THREADS) {
+            const uint4 a = __ldcs(v + i), b = __ldcs(v + i + AW_THREADS), c = __ldcs(v + i + 2 * AW_THREADS), e = __ldcs(v + i + 3 * AW_THREADS);
+            if (a.x != BK_PAD) window_update<KIND>(win, a.x);
+            if (a.y != BK_PAD) window_update<KIND>(win, a.y);
+            if (a.z != BK_PAD) window_update<KIND>(win, a.z);
+            if (a.w != BK_PAD) window_update<KIND>(win, a.w);
+            if (b.x != BK_PAD) window_update<KIND>(win, b.x);
+            if (b.y != BK_PAD) window_update<KIND>(win, b.y);
+            if (b.z != BK_PAD) window_update<KIND>(win, b.z);
+            if (b.w != BK_PAD) window_update<KIND>(win, b.w);
+            if (c.x != BK_PAD) window_update<KIND>(win, c.x);
+            if (c.y != BK_PAD) window_update<KIND>(win, c.y);
+            if (c.z != BK_PAD) window_update<KIND>(win, c.z);
+            if (c.w != BK_PAD) window_update<KIND>(win, c.w);
+            if (e.x != BK_PAD) window_update<KIND>(win, e.x);
+            if (e.y != BK_PAD) window_update<KIND>(win, e.y);
+            if (e.z != BK_PAD) window_update<KIND>(win, e.z);
+            if (e.w != BK_PAD) window_update<KIND>(win, e.w);
+        }
+        for (; i < body; i += AW_THREADS) {
+            const uint4 a = __ldcs(v + i);
+            if (a.x != BK_PAD) window_update<KIND>(win, a.x);
+            if (a.y != BK_PAD) window_update<KIND>(win, a.y);
+            if (a.z != BK_PAD) window_update<KIND>(win, a.z);
+            if (a.w != BK_PAD) window_update<KIND>(win, a.w);
+        }
+        const uint32_t tail0 = head + body * 4;
+        if (tail0 + tid < n) {
+            const uint32_t x = __ldcs(src + tail0 + tid);
+            if (x != BK_PAD) window_update<KIND>(win, x);
+        }
+    }
+    __syncthreads();
+    // merge the image into the table: one coalesced read-modify-write of the window
+    uint4* tbl4 = reinterpret_cast<uint4*>(slice_words_ptr<KIND>(ts, sl.table, sl.slot0) + w_lo);
+    for (uint32_t i = tid; i < nwords / 4; i += AW_THREADS) {
+        const uint4 dlt = win4[i];
+        if ((dlt.x | dlt.y | dlt.z | dlt.w) == 0u) continue;
+        uint4 t = __ldcs(tbl4 + i);
+        t.x = window_merge<KIND>(t.x, dlt.x);
+        t.y = window_merge<KIND>(t.y, dlt.y);
+        t.z = window_merge<KIND>(t.z, dlt.z);
+        t.w = window_merge<KIND>(t.w, dlt.w);
+        __stcs(tbl4 + i, t);
+    }
 }
 
 // Overflow lists received from the peers (rare path): world lists of up to `cap` (table, slot) records.

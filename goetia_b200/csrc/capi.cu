@@ -710,6 +710,8 @@ extern "C" gt_batch* gt_batch_pack(const char* bases, const uint64_t* offsets, u
     bool ok = cudaMemcpy(b->d_offsets, rebased.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMemset(b->d_flags, 0, n_reads + 1) == cudaSuccess;
     ok = ok && cudaMemset(b->d_words + b->n_words, 0, (b->n_words_alloc - b->n_words) * 8) == cudaSuccess;
+    // the copies / memsets above ran on the legacy stream; the slot streams are non-blocking, so order them explicitly
+    ok = ok && cudaDeviceSynchronize() == cudaSuccess;
     // chunk on 32-base boundaries so each chunk fills whole words
     uint64_t lim = chunk_bases() & ~31ull;
     int which = 0;
@@ -1389,6 +1391,18 @@ extern "C" int gt_storage_pending_info(gt_storage* st, uint64_t* info) {
     return 0;
 }
 
+// Synthetic reads for harnesses (kernels.cuh, k_synth_bases): n_bases ASCII bytes of stream `seed` starting at
+// global base index `first_base`, written to device memory on the compute stream.
+extern "C" int gt_synth_bases_dev(void* d_out, uint64_t n_bases, uint64_t seed, uint64_t first_base) {
+    if (ensure_ctx()) return -1;
+    if (n_bases == 0) return 0;
+    if (!d_out || (reinterpret_cast<uintptr_t>(d_out) & 15)) return fail("gt_synth_bases_dev: d_out must be a 16-byte aligned device pointer");
+    CU(cudaSetDevice(g_ctx.device));
+    k_synth_bases<<<grid_for((n_bases + 15) / 16, 256, 8), 256, 0, g_ctx.main>>>(static_cast<uint8_t*>(d_out), n_bases, seed, first_base); ++g_launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+
 extern "C" uint64_t gt_launch_count(void) { return g_launches; }
 
 // Device timing helpers for harnesses: events recorded on the library's compute stream.
@@ -1656,9 +1670,9 @@ extern "C" int gt_insert_hashes(gt_storage* st, const uint64_t* hashes, uint64_t
     if (st->world > 1) return fail("gt_insert_hashes: not available on a sharded storage");
     if (check_mode("gt_insert_hashes", mode)) return -1;
     if (is_new && mode == GT_MODE_BLIND) return fail("gt_insert_hashes: is_new needs GT_MODE_FAST or GT_MODE_EXACT");
-    // is_new must see every earlier insert; and the saturating CAS of a counting storage must not run beside
-    // an optimistic apply (bucket.cuh, K2 for the counting storages)
-    if ((mode != GT_MODE_BLIND || st->kind != 0) && pending_flush_sync(st)) return -1;
+    // is_new must see every earlier insert; and a direct table writer must not run beside an apply that merges
+    // windows into the tables (bucket.cuh, K2w)
+    if (pending_flush_sync(st)) return -1;
     if (n == 0) return 0;
     CU(cudaSetDevice(g_ctx.device));
     const uint64_t chunk = 64ull << 20;  // hashes per chunk

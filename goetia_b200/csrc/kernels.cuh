@@ -751,6 +751,41 @@ __global__ void __launch_bounds__(256) k_checksum(const uint32_t* __restrict__ t
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, mine);
 }
 
+// ------------------------------------------------------------------------------------------
+// Counter-based synthetic reads for harnesses (bench.py, the full-size parity tests): the base at GLOBAL
+// index i of stream `seed` is a pure function of (seed, i), so the same reads exist on the CPU (numpy:
+// goetia_b200/synth.py), on one GPU and on any rank of a sharded run.  word w = i / 32:
+//   z = splitmix64(seed + (w + 1) * 0x9E3779B97F4A7C15);  code(i) = (z >> 2*(i%32)) & 3;  byte = "ACGT"[code]
+// ------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t synth_word(uint64_t seed, uint64_t w) {
+    uint64_t z = seed + (w + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+// one thread = 16 output bytes (out must be 16-byte aligned)
+__global__ void __launch_bounds__(256) k_synth_bases(uint8_t* __restrict__ out, uint64_t n_bases, uint64_t seed, uint64_t first) {
+    const uint64_t n16 = (n_bases + 15) / 16;
+    for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < n16; g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i0 = first + g * 16;
+        uint64_t w = i0 >> 5, z = synth_word(seed, w);
+        uint32_t v[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint64_t i = i0 + j;
+            if ((i >> 5) != w) { w = i >> 5; z = synth_word(seed, w); }
+            const uint32_t code = (uint32_t)(z >> (2 * (i & 31))) & 3u;
+            const uint32_t ch = (0x54474341u >> (8 * code)) & 0xffu;  // "ACGT"
+            v[j >> 2] |= ch << (8 * (j & 3));
+        }
+        if (g * 16 + 16 <= n_bases) {
+            *reinterpret_cast<uint4*>(out + g * 16) = make_uint4(v[0], v[1], v[2], v[3]);
+        } else {
+            for (uint64_t j = 0; g * 16 + j < n_bases; ++j) out[g * 16 + j] = (uint8_t)(v[j >> 2] >> (8 * (j & 3)));
+        }
+    }
+}
+
 // BitStorage::update_from (bitstorage.cc:103-137): dst |= src
 __global__ void __launch_bounds__(256) k_or_tables(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint64_t n_words) {
     for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words; w += (uint64_t)gridDim.x * blockDim.x)

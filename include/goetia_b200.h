@@ -199,6 +199,12 @@ int gt_storage_apply(gt_storage* st);
 int gt_storage_pending_info(gt_storage* st, uint64_t* info);
 /* number of CUDA kernels this library has launched so far in this process */
 uint64_t gt_launch_count(void);
+/* Harness helper (no counterpart in the reference; SURVEY.md section 8d asks for synthetic reads that the CPU
+ * oracle and every GPU rank see byte-identically): write n_bases ASCII bytes of the counter-based synthetic
+ * base stream `seed`, starting at GLOBAL base index first_base, to device memory (16-byte aligned), asynchronously
+ * on the compute stream.  base(i) = "ACGT"[(splitmix64(seed + (i/32 + 1) * 0x9E3779B97F4A7C15) >> 2*(i%32)) & 3];
+ * goetia_b200/synth.py is the numpy twin. */
+int gt_synth_bases_dev(void* d_out, uint64_t n_bases, uint64_t seed, uint64_t first_base);
 /* Device timing for harnesses (the library launches on its own streams, which events of
  * another runtime's stream do not see).  gt_timer_record puts a CUDA event on the compute
  * stream (ordered after everything queued so far); gt_timer_elapsed_ms waits for both. */

@@ -16,15 +16,25 @@ from tests.util import (Port, SHIFTERS, STORAGES, assert_tables_equal, genome_re
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture
-def forced(monkeypatch):
+# How the buckets are applied (bucket.cuh): "atomics" = k_apply (global RED / CAS per update); "win1" = k_apply_win
+# with one shared-memory window per slice; "win2" = k_rebucket into 128-byte windows + k_apply_win (two-level).
+APPLY = {"atomics": ("0", "16"), "win1": ("2", "16"), "win2": ("2", "7")}
+
+
+@pytest.fixture(params=sorted(APPLY))
+def forced(monkeypatch, request):
     """Force the bucket path with tiny slices and a tiny store (many buckets, many flushes)."""
+    mode, wlog2 = APPLY[request.param]
+    monkeypatch.setenv("GT_APPLY_WINDOWS", mode)
+    monkeypatch.setenv("GT_WINDOW_LOG2_BYTES", wlog2)
+
     def set_env(slice_log2=12, entries=1 << 20, min_kmers=0):
         monkeypatch.setenv("GT_BUCKET_FORCE", "1")
         monkeypatch.setenv("GT_SLICE_LOG2_BYTES", str(slice_log2))
         monkeypatch.setenv("GT_PENDING_ENTRIES", str(entries))
         monkeypatch.setenv("GT_BUCKET_MIN_KMERS", str(min_kmers))
     set_env()
+    set_env.apply = request.param
     return set_env
 
 
@@ -211,14 +221,12 @@ def test_big_table_reducers(gb, monkeypatch, x):
 
 
 @pytest.mark.parametrize("kind,_n", [(1, "ByteStorage"), (2, "NibbleStorage")])
-@pytest.mark.parametrize("cas", ["0", "1"])
-def test_bucketed_counting_saturation(gb, forced, monkeypatch, kind, _n, cas):
-    """Counting storages are applied optimistically (plain atomic adds; slices where an add met a counter at its
-    maximum are undone and replayed with the saturating CAS -- bucket.cuh, K2 for the counting storages).  Deep
-    coverage drives many counters through their maximum inside the buckets; tables must still equal the oracle's
-    min(max, hits) byte for byte, over several applies, and the plain CAS apply (GT_APPLY_CAS=1) must agree."""
+def test_bucketed_counting_saturation(gb, forced, monkeypatch, kind, _n):
+    """Counting storages through the window apply: a window's image in shared memory holds the hits of one apply per
+    counter, saturating at the counter's maximum, and is merged with a per-counter saturating add (bucket.cuh, K2w).
+    Deep coverage drives many counters through their maximum inside the buckets AND inside one apply; tables must
+    still equal the oracle's min(max, hits) byte for byte, over several applies, under every apply variant."""
     forced(slice_log2=13, entries=1 << 24)
-    monkeypatch.setenv("GT_APPLY_CAS", cas)
     K = 21
     sizes = gb.get_n_primes_near_x(4, 700_001)
     bases, offsets = genome_reads(30000, 100, 2500, seed=31)  # ~1000x coverage of 2.5 kb: counts far past 255
