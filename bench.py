@@ -50,6 +50,10 @@ WORKLOADS = {
            "C2: dBG<ByteStorage,CanLemireShifter> K=21, ByteStorage(4e9,4), 20M x 150bp synthetic reads (insert)"),
     "c5": (2, 25, int(8e9), 4, 1_000_000, 10_000, 46,
            "C5: dBG<NibbleStorage,CanLemireShifter> K=25, NibbleStorage(8e9,4), 1M x 10kb synthetic reads"),
+    # the query half of C2: insert once (untimed), then time the per-read median-count query over the same reads
+    "c2q": (1, 21, int(4e9), 4, 20_000_000, 150, 43,
+            "C2 query: dBG<ByteStorage,CanLemireShifter> K=21, ByteStorage(4e9,4), per-read median-count query "
+            "(DiginormFilter::median_count_at_least, cutoff 1) over 20M x 150bp synthetic reads after inserting them"),
     # sketch workload (kind -1): not the headline metric; `--workload c4` reports k-mers sketched per second
     "c4": (-1, 31, 1000, 0, 100_000_000, 150, 45,
            "C4: SourmashSketch K=31 scaled=1000 streaming sketch of 100M x 150bp synthetic reads"),
@@ -143,19 +147,44 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def synth_reads_device(torch, n_reads, read_len, seed, device):
-    """Uniform random ACGT reads generated on the device (torch Philox, seed stated in config)."""
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    n = n_reads * read_len
-    out = torch.empty(n, dtype=torch.uint8, device=device)
-    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=device)
-    step = 1 << 26
-    for i in range(0, n, step):
-        m = min(step, n - i)
-        codes = torch.randint(0, 4, (m,), dtype=torch.int64, device=device, generator=g)
-        out[i:i + m] = lut[codes]
+def synth_reads_device(torch, L, first_read, n_reads, read_len, seed, device):
+    """Reads [first_read, first_read + n_reads) of the counter-based synthetic stream `seed` (goetia_b200/synth.py is the
+    numpy twin; the CPU reference and every rank see the same bytes), written on the device by gt_synth_bases_dev."""
+    from goetia_b200 import _capi
+    out = torch.empty(max(n_reads, 1) * read_len + 16, dtype=torch.uint8, device=device)
+    torch.cuda.synchronize()
+    _capi.check(L.gt_synth_bases_dev(out.data_ptr(), n_reads * read_len, seed, first_read * read_len), "gt_synth_bases_dev")
+    L.gt_synchronize()
     return out
+
+
+def golden_entry(workload, reads, total_default):
+    """Reference-pinned table checksums of the full-size workload (tests/golden/fullsize_golden.json, made by
+    tests/golden/make_fullsize_golden.py from the compiled, unmodified reference) -- only for the unmodified read set."""
+    if reads != total_default:
+        return None
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "fullsize_golden.json")) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
+def checksum_check(gold, sums, n_occ):
+    """check block: the tables' position-weighted checksums (computed in HBM, all ranks summed) against the reference's."""
+    if gold is None:
+        return {"tables_checksum_equal_reference": None, "note": "no golden entry for this read count / workload"}
+    ok = [int(a) == int(b) for a, b in zip(sums, gold["checksums"])]
+    return {"tables_checksum_equal_reference": bool(all(ok)) and int(n_occ) == int(gold["n_occupied"]),
+            "n_occupied_reference": int(gold["n_occupied"]), "checksums": [int(x) for x in sums],
+            "reference": "tests/golden/fullsize_golden.json (oracle/_ref, the unmodified reference, %d thread(s), same counter-based reads)"
+                         % gold.get("threads", 1)}
+
+
+def measured_r_rand(L, what, footprint_bytes):
+    """The random-sector roofline, measured in this run on this device (gt_probe_random)."""
+    v = L.gt_probe_random(what, int(footprint_bytes), 1 << 28)
+    return float(v) if v > 0 else None
 
 
 def cpu_reference_modes(kind, K, sizes, threads):
@@ -237,23 +266,34 @@ def main():
         return multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_reads)
 
     # ---- inputs: resident ASCII sub-batches ------------------------------------------------------
+    total_default = WORKLOADS[args.workload][4]
+    gold = golden_entry("c2" if args.workload == "c2q" else args.workload, total_reads, total_default)
     reads_per_sub = max(1, min(total_reads, SUB_BATCH_BASES // read_len))
+    reads_per_sub -= reads_per_sub % 16 if reads_per_sub > 16 else 0
     subs = []
     r = 0
     while r < total_reads:
         n = min(reads_per_sub, total_reads - r)
-        subs.append((synth_reads_device(torch, n, read_len, seed + 1000 * len(subs), dev), n))
+        subs.append((synth_reads_device(torch, L, r, n, read_len, seed, dev), n))
         r += n
     offs = torch.arange(reads_per_sub + 1, dtype=torch.int64, device=dev) * read_len
     torch.cuda.synchronize()
     storage = [gb.BitStorage, gb.ByteStorage, gb.NibbleStorage][kind](sizes)
     graph = gb.dBG[type(storage), gb.CanLemireShifter].build(storage, K)
+    if args.workload == "c2q":
+        return query_arm(args, torch, gb, _capi, L, dev, local_rank, storage, graph, subs, offs, sizes, gold, K, read_len,
+                         total_reads, seed, desc)
+    # counting storages start every step from empty tables (a saturated table would hide the first-pass cost);
+    # a Bloom table is idempotent, so C3 / C1 keep accumulating
+    reset_each_step = kind != 0
 
     d_total = torch.zeros(1, dtype=torch.int64, device=dev)  # k-mers consumed, accumulated on the device
     torch.cuda.synchronize()
 
     def step_resident():
         # nothing in here waits for the GPU until the flush at the end of the step
+        if reset_each_step:
+            storage.reset()
         for b, n in subs:
             graph.insert_sequences_dev_async(b.data_ptr(), offs.data_ptr(), n, n * read_len, mode=gb.MODE_BLIND,
                                              d_kmer_total_ptr=d_total.data_ptr())
@@ -287,13 +327,16 @@ def main():
     L.gt_profile_enable(0)
     value = kmers_per_step * args.steps / (ms / 1e3)
 
-    # ---- property check at full size (the oracle cannot run 6e9 k-mers in bench time) -----------
+    # ---- parity at full size: table checksums against the compiled reference's (same reads) -----------------
     info = storage.pending_info()
+    n_occ = storage.n_occupied()
+    sums = [storage.checksum(i) for i in range(n_tables)]
+    check = checksum_check(gold, sums, n_occ)
     sample_b = subs[0][0][:2000 * read_len].cpu().numpy()
     sample_o = np.arange(2001, dtype=np.uint64) * np.uint64(read_len)
     q = graph.query_sequences(sample_b, sample_o)
-    present = bool((q >= 1).all())
-    n_occ = storage.n_occupied()
+    check["sample_reads_all_present"] = bool((q >= 1).all())
+    check["n_occupied"] = n_occ
 
     # ---- e2e: host buffers through the C ABI ------------------------------------------------------
     e2e = None
@@ -302,7 +345,7 @@ def main():
         host_b = torch.empty(total_reads * read_len, dtype=torch.uint8, pin_memory=True)
         p = 0
         for b, n in subs:
-            host_b[p:p + n * read_len].copy_(b)
+            host_b[p:p + n * read_len].copy_(b[:n * read_len])
             p += n * read_len
         host_o = torch.empty(total_reads + 1, dtype=torch.int64, pin_memory=True)
         host_o.copy_(torch.arange(total_reads + 1, dtype=torch.int64) * read_len)
@@ -311,6 +354,8 @@ def main():
         os.environ.setdefault("GT_CHUNK_BASES", str(256 << 20))
 
         def step_host():
+            if reset_each_step:
+                storage.reset()
             nk = graph.insert_sequences(hb, ho, mode=gb.MODE_BLIND)  # returns the k-mer count read back from the device
             storage.flush()
             return nk
@@ -330,18 +375,17 @@ def main():
 
     # ---- roofline -----------------------------------------------------------------------------------
     peak, peak_src = measured_peak()
-    roofline = insert_roofline(prof_ms, prof_n, ms, kmers_per_step * args.steps, n_tables, peak, peak_src, args.workload)
+    table_bytes = sum(storage.table_bytes(i) for i in range(n_tables))
+    r_rand = measured_r_rand(L, 0, table_bytes)
+    roofline = insert_roofline(prof_ms, prof_n, ms, kmers_per_step * args.steps, n_tables, peak, peak_src, args.workload, r_rand,
+                               table_bytes)
 
     # ---- CPU baseline ---------------------------------------------------------------------------------
     cpu = None
     if not args.no_cpu_baseline:
+        from goetia_b200.synth import synth_reads
         nb = min(total_reads, 4_000_000)
-        if host_b is not None:
-            cb = host_b.numpy()[:nb * read_len]
-        else:
-            cb = subs[0][0][:nb * read_len].cpu().numpy()
-            nb = cb.size // read_len
-        co = np.arange(nb + 1, dtype=np.uint64) * np.uint64(read_len)
+        cb, co = synth_reads(seed, 0, nb, read_len)  # the same bytes the GPU path was fed
         del storage, graph
         cpu = cpu_reference_rate(kind, K, sizes, cb, co, budget_s=15.0, threads=os.cpu_count() or 1)
 
@@ -354,19 +398,19 @@ def main():
                    "kmers_per_step": kmers_per_step, "mode": "GT_MODE_BLIND (write-combined)",
                    "sub_batches": len(subs), "slice_shift": info["slice_shift"], "n_buckets": info["n_buckets"],
                    "pending_entries": info["entries"], "bucket_overflow_updates": info["n_direct"],
-                   "seed": seed, "generator": "torch.randint on device (Philox)",
+                   "seed": seed, "generator": "counter-based splitmix64 (gt_synth_bases_dev / goetia_b200/synth.py)",
                    "l2": "inputs larger than L2 (%.1f GB reads + %.1f GB tables + %.1f GB update store per step)"
-                         % (total_reads * read_len / 1e9, sum(sizes) / 8e9 if kind == 0 else sum(sizes) / 1e9,
-                            info["entries"] * 4 / 1e9),
-                   "tables": "accumulate across steps (no reset): RED.OR / saturating-CAS work is the same on a full table"},
+                         % (total_reads * read_len / 1e9, table_bytes / 1e9, info["entries"] * 4 / 1e9),
+                   "tables": "reset at the start of every step (counting storage: every step is a first pass)" if reset_each_step
+                             else "accumulate across steps (a Bloom table is idempotent; the work per step is the same)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-        "check": {"sample_reads_all_present": present, "n_occupied": n_occ},
+        "check": check,
     }
     print(json.dumps(out))
     return 0
 
 
-def insert_roofline(prof_ms, prof_n, step_ms_total, kmers, n_tables, peak, peak_src, workload):
+def insert_roofline(prof_ms, prof_n, step_ms_total, kmers, n_tables, peak, peak_src, workload, r_rand=None, table_bytes=0):
     """HBM roofline of the insert (64 B algorithmic per (k-mer, table)).
 
     On the write-combined path the insert is the kernel PAIR k_bucket (hash + bucket by table slice) ->
@@ -377,7 +421,7 @@ def insert_roofline(prof_ms, prof_n, step_ms_total, kmers, n_tables, peak, peak_
     bytes ncu measured for one launch pair (profiles/traffic.json) -- far below the algorithmic bytes, which is
     the point of write-combining and why `frac` can exceed 1: the limiters are instruction issue (k_bucket) and
     L2 atomic throughput (k_apply), see `dram_frac` and DESIGN.md section 3."""
-    names = ("k_bucket", "k_apply", "k_walk")
+    names = ("k_bucket", "k_apply (k_rebucket + k_apply_win)", "k_walk")
     algo_bytes = ALGO_BYTES_PER_KMER_PER_TABLE * n_tables
     combined = bool(prof_n[1])
     achieved = kmers * algo_bytes / (step_ms_total / 1e3) / 1e9 if step_ms_total > 0 else 0.0
@@ -390,7 +434,7 @@ def insert_roofline(prof_ms, prof_n, step_ms_total, kmers, n_tables, peak, peak_
         pass
     out = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
            "traffic": traffic, "peak_source": peak_src,
-           "kernel": "k_bucket + k_apply (write-combined insert, concurrent on two streams)" if combined else "k_walk",
+           "kernel": "k_bucket + k_rebucket + k_apply_win (write-combined insert, two streams)" if combined else "k_walk",
            "algorithmic_bytes_per_kmer": algo_bytes,
            "kernels": {name: {"launches": int(prof_n[i]), "ms_total": float(prof_ms[i]),
                               "ms_per_launch": float(prof_ms[i] / max(1, int(prof_n[i]))),
@@ -403,13 +447,149 @@ def insert_roofline(prof_ms, prof_n, step_ms_total, kmers, n_tables, peak, peak_
         out["traffic_detail"] = detail
         out["dram_bytes_per_kmer_measured"] = per_kmer
         out["dram_frac"] = per_kmer * kmers / (step_ms_total / 1e3) / 1e9 / peak if step_ms_total > 0 else None
-    # the random-sector roofline north_star's ">= 50 %" refers to: independent random 32-bit RED.OR over a
-    # footprint >> L2, measured on this pool's B200 (profiles/r1_microbench_b200.jsonl, scripts/microbench.cu)
-    r_rand = 20.2e9
-    out["random_sector_roofline"] = {"r_rand_atomics_per_s": r_rand,
-                                     "achieved_updates_per_s": kmers * n_tables / (step_ms_total / 1e3) if step_ms_total > 0 else 0.0,
-                                     "frac": kmers * n_tables / (step_ms_total / 1e3) / r_rand if step_ms_total > 0 else 0.0}
+    # the random-sector roofline north_star's ">= 50 %" refers to: independent random 32-bit RED.OR over a footprint
+    # equal to the tables', MEASURED IN THIS RUN on this device (gt_probe_random; scripts/microbench.cu is the long form)
+    if r_rand:
+        out["random_sector_roofline"] = {"r_rand_atomics_per_s": r_rand, "measured": "in this run, footprint = the tables' %.1f GB" % (table_bytes / 1e9),
+                                         "achieved_updates_per_s": kmers * n_tables / (step_ms_total / 1e3) if step_ms_total > 0 else 0.0,
+                                         "frac": kmers * n_tables / (step_ms_total / 1e3) / r_rand if step_ms_total > 0 else 0.0}
+    out["traffic_source"] = "ncu capture by the builder, committed under profiles/ (see profiles/traffic.json)"
     return out
+
+
+def query_arm(args, torch, gb, _capi, L, dev, local_rank, storage, graph, subs, offs, sizes, gold, K, read_len, total_reads, seed, desc):
+    """`--workload c2q`: the query half of BASELINE.json configs[1] -- DiginormFilter::median_count_at_least per read
+    (diginorm.hh:35-68 over dBG::query_sequence, dbg.hh:349-362) on the C2 graph.  Reads are inserted once (untimed,
+    tables checked against the reference's checksums); a step = one pass of the median-count query over all reads.
+    Algorithmic bytes: n_tables x 32 B sector reads = 128 B per k-mer."""
+    n_tables = len(sizes)
+    kpr = read_len - K + 1
+    kmers_per_step = total_reads * kpr
+    for b, n in subs:
+        graph.insert_sequences_dev_async(b.data_ptr(), offs.data_ptr(), n, n * read_len, mode=gb.MODE_BLIND)
+    storage.flush()
+    n_occ = storage.n_occupied()
+    check = checksum_check(gold, [storage.checksum(i) for i in range(n_tables)], n_occ)
+    d_total = torch.zeros(1, dtype=torch.int64, device=dev)
+    d_pass = [torch.zeros(n, dtype=torch.uint8, device=dev) for _, n in subs]
+    torch.cuda.synchronize()
+    cutoff = 1
+
+    def step():
+        for (b, n), dp in zip(subs, d_pass):
+            _capi.check(L.gt_median_count_at_least_dev(storage.handle, _capi.SHIFTER_CAN, K, b.data_ptr(), offs.data_ptr(), n,
+                                                       n * read_len, cutoff, dp.data_ptr(), d_total.data_ptr()),
+                        "gt_median_count_at_least_dev")
+
+    for _ in range(args.warmup):
+        d_total.zero_()
+        torch.cuda.synchronize()
+        step()
+        L.gt_synchronize()
+        assert int(d_total.item()) == kmers_per_step
+    _capi.check(L.gt_profile_enable(1), "gt_profile_enable")
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = L.gt_launch_count()
+    _capi.check(L.gt_timer_record(0), "gt_timer_record")
+    for _ in range(args.steps):
+        step()
+    _capi.check(L.gt_timer_record(1), "gt_timer_record")
+    ms = L.gt_timer_elapsed_ms(0, 1)
+    L.gt_synchronize()
+    launches = int(L.gt_launch_count() - launches0)
+    clocks = sampler.stop()
+    prof_ms, prof_n = np.zeros(3, dtype=np.float64), np.zeros(3, dtype=np.uint64)
+    _capi.check(L.gt_profile_get(prof_ms.ctypes.data, prof_n.ctypes.data), "gt_profile_get")
+    L.gt_profile_enable(0)
+    value = kmers_per_step * args.steps / (ms / 1e3)
+    check["all_reads_pass_cutoff_1"] = bool(all(int(dp.sum().item()) == n for dp, (_, n) in zip(d_pass, subs)))
+
+    e2e = None
+    if not args.no_e2e:
+        host_b = torch.empty(total_reads * read_len, dtype=torch.uint8, pin_memory=True)
+        p = 0
+        for b, n in subs:
+            host_b[p:p + n * read_len].copy_(b[:n * read_len])
+            p += n * read_len
+        host_o = torch.empty(total_reads + 1, dtype=torch.int64, pin_memory=True)
+        host_o.copy_(torch.arange(total_reads + 1, dtype=torch.int64) * read_len)
+        host_p = torch.empty(total_reads, dtype=torch.uint8, pin_memory=True)
+        torch.cuda.synchronize()
+        hb, ho, hp = host_b.numpy(), host_o.numpy().view(np.uint64), host_p.numpy()
+
+        def step_host():
+            nk = L.gt_median_count_at_least(storage.handle, _capi.SHIFTER_CAN, K, hb.ctypes.data, ho.ctypes.data, total_reads, cutoff,
+                                            hp.ctypes.data, None)
+            return _capi.check(nk, "gt_median_count_at_least")
+
+        assert step_host() == kmers_per_step
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host()
+        L.gt_synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {"value": kmers_per_step * args.steps / dt, "unit": "k-mers/s", "h2d_bytes_per_step": int(hb.nbytes + ho.nbytes),
+               "d2h_bytes_per_step": int(hp.nbytes) + 8, "ms_per_step": dt * 1e3 / args.steps,
+               "api": "gt_median_count_at_least(host ASCII, host offsets) -> pass[read] in pinned host memory"}
+        check["e2e_all_reads_pass_cutoff_1"] = bool(hp.all())
+
+    peak, peak_src = measured_peak()
+    table_bytes = sum(storage.table_bytes(i) for i in range(n_tables))
+    r_load = measured_r_rand(L, 1, table_bytes)
+    algo = 32 * n_tables
+    achieved = kmers_per_step * args.steps * algo / (ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "kernel": "k_walk<OP_MEDIAN> (direct random 32 B sector loads, 4 per k-mer)",
+                "algorithmic_bytes_per_kmer": algo,
+                "kernels": {"k_walk": {"launches": int(prof_n[2]), "ms_total": float(prof_ms[2]),
+                                       "ms_per_launch": float(prof_ms[2] / max(1, int(prof_n[2]))),
+                                       "share_of_step": float(prof_ms[2] / ms) if ms > 0 else 0.0}},
+                "random_sector_roofline": None if not r_load else {
+                    "r_rand_loads_per_s": r_load, "measured": "in this run, random 32 B loads over %.1f GB" % (table_bytes / 1e9),
+                    "achieved_loads_per_s": kmers_per_step * args.steps * n_tables / (ms / 1e3),
+                    "frac": kmers_per_step * args.steps * n_tables / (ms / 1e3) / r_load}}
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get("c2q")
+        if t:
+            roofline["traffic"] = float(t["k_walk"])
+            roofline["traffic_detail"] = t
+    except Exception:
+        pass
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        from goetia_b200.synth import synth_reads
+        from oracle import binding
+        del storage, graph
+        impl = binding.Ref(1, 1, K, sizes) if binding.have_ref() else binding.Port(1, 1, K, sizes)
+        kname = "reference" if binding.have_ref() else "port"
+        nb = 200_000
+        cb, co = synth_reads(seed, 0, nb, read_len)
+        impl.insert_reads(cb, co)
+        t0, nq, budget = time.perf_counter(), 0, 15.0
+        for r_ in range(nb):
+            impl.median_count_at_least(cb[r_ * read_len:(r_ + 1) * read_len].tobytes(), cutoff)
+            nq += 1
+            if (nq & 1023) == 0 and time.perf_counter() - t0 > budget:
+                break
+        secs = time.perf_counter() - t0
+        impl.close()
+        cpu = {"value": nq * kpr / secs, "unit": "k-mers/s", "cores": 1, "kind": kname,
+               "sample": "DiginormFilter::median_count_at_least per read over %d reads (%d k-mers) of the same set on full-size "
+                         "tables holding the first %d reads, %.1f s, one thread" % (nq, nq * kpr, nb, secs)}
+
+    out = {"metric": "k-mers queried/sec (device-timed)", "value": value, "unit": "k-mers/s", "n_gpus": 1, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+           "config": {"workload": desc if not args.reads else desc + " [reads overridden: %d]" % total_reads, "K": K,
+                      "tablesizes": sizes, "reads": total_reads, "read_len": read_len, "kmers_per_step": kmers_per_step,
+                      "cutoff": cutoff, "seed": seed, "generator": "counter-based splitmix64 (gt_synth_bases_dev / goetia_b200/synth.py)",
+                      "l2": "inputs larger than L2 (%.1f GB reads, %.1f GB tables)" % (total_reads * read_len / 1e9, table_bytes / 1e9)},
+           "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "check": check}
+    print(json.dumps(out))
+    return 0
 
 
 def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_reads):
@@ -429,10 +609,14 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
     rounds = max(2, -(-max_rank_reads * read_len // round_bases))
     per_round = -(-max_rank_reads // rounds)
     st = ShardedStorage(kind, sizes, per_round * read_len)
+    # rank r holds a contiguous range of the SAME global read set the single-GPU run (and the CPU reference) sees
+    first_read = rank * (total_reads // world) + min(rank, total_reads % world)
+    gold = golden_entry(args.workload, total_reads, WORKLOADS[args.workload][4])
+    reset_each_step = kind != 0
     subs, r = [], 0
     for i in range(rounds):  # every rank runs the same number of rounds (the exchange is collective)
         n = max(0, min(per_round, reads_rank - r))
-        subs.append((synth_reads_device(torch, max(n, 1), read_len, seed + 1000 * i + 100000 * rank, dev), n))
+        subs.append((synth_reads_device(torch, L, first_read + r, n, read_len, seed, dev), n))
         r += n
     offs = torch.arange(per_round + 1, dtype=torch.int64, device=dev) * read_len
     torch.cuda.synchronize()
@@ -442,6 +626,8 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
 
     def step():
         # no host wait anywhere in a step: rounds are queued back to back on the two streams
+        if reset_each_step:
+            st.reset()
         for b, n in subs:
             if n:
                 st.bucket_sequences_dev_async(_capi.SHIFTER_CAN, K, b.data_ptr(), offs.data_ptr(), n, n * read_len,
@@ -484,6 +670,8 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
     value = kmers_per_step * args.steps / (ms / 1e3)
     info = st.pending_info()  # raises if any update was dropped
     n_occ = st.n_occupied()
+    check = checksum_check(gold, [st.checksum(i) for i in range(n_tables)], n_occ)  # collective: the shards' sums add up
+    check["n_occupied_all_ranks"] = n_occ
 
     # e2e: pinned host reads -> H2D inside the timed region -> bucket -> exchange -> apply; wall clock, max over ranks
     e2e = None
@@ -507,6 +695,8 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
             # starts as soon as it has landed, so only the first piece of a step is exposed.  The exchange and
             # k_apply (apply stream) stay per round.  One result read-back (the k-mer count) ends the step.
             consumed = [None, None]
+            if reset_each_step:
+                st.reset()
             with torch.cuda.stream(st.stream):
                 d_total.zero_()
             for i, (h, (b, n)) in enumerate(zip(hosts, subs)):
@@ -572,10 +762,10 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
                        "transport": st.transport,
                        "rounds_per_step": rounds, "slice_shift": info["slice_shift"], "n_buckets": info["n_buckets"],
                        "bucket_overflow_updates": info["n_direct"], "seed": seed,
-                       "generator": "torch.randint on device (Philox), per-rank seeds",
+                       "generator": "counter-based splitmix64 (gt_synth_bases_dev / goetia_b200/synth.py); rank r holds a contiguous range of the one global read set",
                        "l2": "inputs larger than L2 (per rank: %.1f GB reads, %.1f GB exchange buffers)"
                              % (reads_rank * read_len / 1e9, info["entries"] * 4 / 1e9),
-                       "tables": "accumulate across steps (no reset)"},
+                       "tables": "reset at the start of every step" if reset_each_step else "accumulate across steps (Bloom tables are idempotent)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
@@ -585,7 +775,7 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
                                             "share_of_step": float(prof_ms[i] / ms) if ms > 0 else 0.0}
                                      for i, name in enumerate(("k_bucket", "k_apply")) if prof_n[i]}},
             "cpu_baseline": None,
-            "check": {"n_occupied_all_ranks": n_occ},
+            "check": check,
         }
         print(json.dumps(out))
     st.close()
@@ -604,10 +794,11 @@ def sketch_arm(args, rank, world, local_rank, torch, gb, _capi):
     kpr = read_len - K + 1
     reads_rank = total_reads // world + (1 if rank < total_reads % world else 0)
     reads_per_sub = max(1, min(reads_rank, SUB_BATCH_BASES // read_len))
+    first_read = rank * (total_reads // world) + min(rank, total_reads % world)
     subs, r = [], 0
     while r < reads_rank:
         n = min(reads_per_sub, reads_rank - r)
-        subs.append((synth_reads_device(torch, n, read_len, seed + 1000 * len(subs) + 100000 * rank, dev), n))
+        subs.append((synth_reads_device(torch, L, first_read + r, n, read_len, seed, dev), n))
         r += n
     offs = torch.arange(reads_per_sub + 1, dtype=torch.int64, device=dev) * read_len
     torch.cuda.synchronize()
@@ -653,9 +844,9 @@ def sketch_arm(args, rank, world, local_rank, torch, gb, _capi):
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         from oracle.binding import PortSketch
+        from goetia_b200.synth import synth_reads
         nb = min(reads_rank, 150_000)
-        cb = subs[0][0][:nb * read_len].cpu().numpy()
-        co = np.arange(nb + 1, dtype=np.uint64) * np.uint64(read_len)
+        cb, co = synth_reads(seed, 0, nb, read_len)
         o = PortSketch(0, K, 42, scaled=scaled)
         nk, secs = o.add_reads(cb, co)
         cpu = {"value": nk / secs, "unit": "k-mers/s", "cores": 1, "kind": "port",
@@ -747,13 +938,14 @@ def reference_arm(args, rank, world, kind, K, x, n_tables, total_reads, read_len
     threads = os.cpu_count() or 1
     sizes = binding.Port.primes_near(n_tables, x)
     impl, kname, modes = cpu_reference_modes(kind, K, sizes, threads)
-    rng = np.random.default_rng(seed)
+    from goetia_b200.synth import synth_reads
     kpr = read_len - K + 1
+    cursor = [0]
 
-    def make(n):
-        codes = rng.integers(0, 4, n * read_len, dtype=np.uint8)
-        return (np.frombuffer(b"ACGT", dtype=np.uint8)[codes],
-                np.arange(n + 1, dtype=np.uint64) * np.uint64(read_len))
+    def make(n):  # the next n reads of the workload's own read stream: every call inserts reads never seen before
+        b, o = synth_reads(seed, cursor[0], n, read_len)
+        cursor[0] += n
+        return b, o
 
     def run(b, o, t):
         return cpu_time_reads(impl, kname, b, o, 0, o.size - 1, t)

@@ -90,6 +90,9 @@ SIGNATURES = {
     "gt_set_apply_stream": (C.c_int, [C.c_void_p]),
     "gt_launch_count": (C.c_uint64, []),
     "gt_synth_bases_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "gt_probe_random": (C.c_double, [C.c_int, C.c_uint64, C.c_uint64]),
+    "gt_median_count_at_least_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
+                                               C.c_uint32, C.c_void_p, C.c_void_p]),
     "gt_timer_record": (C.c_int, [C.c_int]),
     "gt_timer_elapsed_ms": (C.c_double, [C.c_int, C.c_int]),
     "gt_profile_enable": (C.c_int, [C.c_int]),

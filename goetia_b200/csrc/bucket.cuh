@@ -506,8 +506,8 @@ __device__ __forceinline__ void counter_addr(uint32_t off, uint32_t& word, uint3
 // k_rebucket (which runs before any window of that apply), and the direct writers (k_walk, k_insert_hashes) are
 // ordered against the apply stream (direct_begin / direct_end).
 // ------------------------------------------------------------------------------------------
-constexpr int RB_THREADS = 512;
-constexpr int RB_PER_THREAD = AP_CHUNK / RB_THREADS;  // 16
+constexpr int RB_THREADS = 1024;
+constexpr int RB_PER_THREAD = AP_CHUNK / RB_THREADS;  // 8
 constexpr int AW_THREADS = 512;
 constexpr int WIN_MAX_PER_SLICE = 1024;
 
@@ -540,13 +540,17 @@ __device__ __forceinline__ uint32_t item_of_chunk(const uint32_t* __restrict__ c
     return *s_b;
 }
 
-// shared memory: sorted[AP_CHUNK] | hist[nw] | lbase[nw] | gdelta[nw] | warp_sums[16]
+// shared memory: sorted[AP_CHUNK] | hist[nw_max + 1] | lbase[nw_max + 1] | gbase[nw_max + 1]
+// One CTA = one 8192-entry chunk of one level-1 item; thread t holds 8 entries in registers.  Pad entries count
+// as window `nw` (one extra histogram bin, sorted to the end and never written out), so the per-entry code has no
+// branches.  The overflow check is per (chunk, window) at reservation time; the per-entry check runs only in a
+// chunk that hit a full sub-bucket.
 template <int KIND>
-__global__ void __launch_bounds__(RB_THREADS)
+__global__ void __launch_bounds__(RB_THREADS, 2)
 k_rebucket(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ items, const uint32_t* __restrict__ chunk_start,
            int n_items, int items_per_slice, const SliceWin* __restrict__ slices, int wshift, int nw_max) {
     extern __shared__ __align__(16) uint32_t rb_sm[];
-    __shared__ uint32_t s_b;
+    __shared__ uint32_t s_b, s_ovf, wsum[RB_THREADS / 32];
     const uint32_t b = item_of_chunk(chunk_start, n_items, &s_b);
     const ApplyItem it = items[b];
     const uint32_t fill = min(__ldcg(it.fill), it.cap);
@@ -556,71 +560,81 @@ k_rebucket(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ it
     const uint32_t nw = sl.n_win;
     uint32_t* sorted = rb_sm;
     uint32_t* hist = rb_sm + AP_CHUNK;
-    uint32_t* lbase = hist + nw_max;
-    uint32_t* gdelta = lbase + nw_max;
-    uint32_t* wsum = gdelta + nw_max;
+    uint32_t* lbase = hist + nw_max + 1;
+    uint32_t* gbase = lbase + nw_max + 1;
     const int tid = threadIdx.x;
-    for (uint32_t d = tid; d < nw; d += RB_THREADS) hist[d] = 0;
+    if ((uint32_t)tid < nw) hist[tid] = 0;
+    if (tid == 0) { hist[nw] = 0; s_ovf = 0; }
     __syncthreads();
     const uint32_t n = min((uint32_t)AP_CHUNK, fill - e0);
     const uint32_t* src = it.src + e0;
     uint32_t v[RB_PER_THREAD], r[RB_PER_THREAD];
-    const bool vec = n == AP_CHUNK && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    if (n == AP_CHUNK && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
 #pragma unroll
-    for (int k = 0; k < RB_PER_THREAD / 4; ++k) {
-        if (vec) {
+        for (int k = 0; k < RB_PER_THREAD / 4; ++k) {
             const uint4 x = __ldcs(reinterpret_cast<const uint4*>(src) + k * RB_THREADS + tid);
             v[4 * k] = x.x; v[4 * k + 1] = x.y; v[4 * k + 2] = x.z; v[4 * k + 3] = x.w;
-        } else {
+        }
+    } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t e = (uint32_t)(k * 4 + j) * RB_THREADS + tid;
-                v[4 * k + j] = e < n ? __ldcs(src + e) : BK_PAD;
-            }
+        for (int k = 0; k < RB_PER_THREAD; ++k) {
+            const uint32_t e = (uint32_t)k * RB_THREADS + tid;
+            v[k] = e < n ? __ldcs(src + e) : BK_PAD;
         }
     }
 #pragma unroll
-    for (int k = 0; k < RB_PER_THREAD; ++k)
-        if (v[k] != BK_PAD) r[k] = atomicAdd(&hist[v[k] >> wshift], 1u);
+    for (int k = 0; k < RB_PER_THREAD; ++k) r[k] = atomicAdd(&hist[min(v[k] >> wshift, nw)], 1u);
     __syncthreads();
-    // exclusive scan of hist over nw (<= 1024) windows: thread t owns windows 2t, 2t+1
-    uint32_t h0 = 0, h1 = 0;
-    if (2u * tid < nw) h0 = hist[2 * tid];
-    if (2u * tid + 1 < nw) h1 = hist[2 * tid + 1];
-    uint32_t incl = h0 + h1;
+    // exclusive scan of hist[0 .. nw] (nw + 1 <= 1025 bins; bin nw = pads, handled by the last thread too)
+    const uint32_t h = (uint32_t)tid < nw ? hist[tid] : 0u;
+    uint32_t incl = h;
+#pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
         if ((tid & 31) >= o) incl += t;
     }
     if ((tid & 31) == 31) wsum[tid >> 5] = incl;
     __syncthreads();
-    uint32_t run = incl - (h0 + h1);
-    for (int w = 0; w < (tid >> 5); ++w) run += wsum[w];
-    // one reservation per (chunk, window) that received entries
-    if (2u * tid < nw) {
-        lbase[2 * tid] = run;
-        gdelta[2 * tid] = h0 ? atomicAdd(sl.sub_fill + 2 * tid, h0) - run : 0u;
+    if (tid < 32) {
+        const uint32_t w = wsum[tid];
+        uint32_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (tid >= o) wi += t;
+        }
+        wsum[tid] = wi - w;  // exclusive
     }
-    if (2u * tid + 1 < nw) {
-        lbase[2 * tid + 1] = run + h0;
-        gdelta[2 * tid + 1] = h1 ? atomicAdd(sl.sub_fill + 2 * tid + 1, h1) - (run + h0) : 0u;
+    __syncthreads();
+    const uint32_t excl = wsum[tid >> 5] + incl - h;
+    if ((uint32_t)tid < nw) {
+        lbase[tid] = excl;
+        uint32_t g = 0;
+        if (h) {  // one reservation per (chunk, window) that received entries
+            g = atomicAdd(sl.sub_fill + tid, h);
+            if (g + h > sl.cap2) s_ovf = 1;
+        }
+        gbase[tid] = (uint32_t)tid * sl.cap2 + g - excl;
     }
+    if (tid == RB_THREADS - 1) lbase[nw] = excl + h;  // == number of real entries (nw < RB_THREADS: h is 0 here unless nw == 1024)
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < RB_PER_THREAD; ++k)
-        if (v[k] != BK_PAD) sorted[lbase[v[k] >> wshift] + r[k]] = v[k];
+    for (int k = 0; k < RB_PER_THREAD; ++k) sorted[lbase[min(v[k] >> wshift, nw)] + r[k]] = v[k];
     __syncthreads();
-    // total valid entries = exclusive base of the last window + its count
-    const uint32_t total = lbase[nw - 1] + hist[nw - 1];
+    const uint32_t total = lbase[nw];
     const uint32_t wmask = (1u << wshift) - 1u;
-    for (uint32_t j = tid; j < total; j += RB_THREADS) {
-        const uint32_t x = sorted[j];
-        const uint32_t d = x >> wshift;
-        const uint32_t pos = j + gdelta[d];
-        if (pos < sl.cap2) {
-            sl.sub[(size_t)d * sl.cap2 + pos] = x & wmask;
-        } else {  // sub-bucket full (skewed input): apply here; no window of this apply has started yet
-            slot_insert<KIND, false>(ts.ptr[sl.table], sl.slot0 + x);
+    if (!s_ovf) {
+        for (uint32_t j = tid; j < total; j += RB_THREADS) {
+            const uint32_t x = sorted[j];
+            sl.sub[gbase[x >> wshift] + j] = x & wmask;
+        }
+    } else {  // some sub-bucket is full (skewed input): the excess is applied here; no window of this apply has started yet
+        for (uint32_t j = tid; j < total; j += RB_THREADS) {
+            const uint32_t x = sorted[j];
+            const uint32_t d = x >> wshift;
+            const uint32_t at = gbase[d] + j;
+            if (at - d * sl.cap2 < sl.cap2) sl.sub[at] = x & wmask;
+            else slot_insert<KIND, false>(ts.ptr[sl.table], sl.slot0 + x);
         }
     }
 }

@@ -1570,6 +1570,95 @@ extern "C" int64_t gt_median_count_at_least(gt_storage* st, int shifter, int K, 
     return (int64_t)g_ctx.h_scratch[3];
 }
 
+// Random-access roofline probe (kernels.cuh, k_probe_random): ops/s of independent random 32-bit RED.OR (what = 0)
+// or random 32 B sector loads (what = 1) over a scratch footprint of footprint_bytes, device-timed (best of 3).
+extern "C" double gt_probe_random(int what, uint64_t footprint_bytes, uint64_t n_ops) {
+    if (ensure_ctx()) return -1.0;
+    if (what < 0 || what > 1 || footprint_bytes < 4096 || n_ops == 0) { fail("gt_probe_random: bad argument"); return -1.0; }
+    if (cudaSetDevice(g_ctx.device) != cudaSuccess) { fail("gt_probe_random: cudaSetDevice failed"); return -1.0; }
+    uint32_t* buf = nullptr;
+    if (cudaMalloc(&buf, footprint_bytes) != cudaSuccess) { cudaGetLastError(); fail("gt_probe_random: out of device memory"); return -1.0; }
+    cudaMemsetAsync(buf, 0, footprint_bytes, g_ctx.main);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    const int grid = g_ctx.sms * 8;
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {  // rep 0 warms up
+        cudaEventRecord(a, g_ctx.main);
+        if (what == 0) k_probe_random<0><<<grid, 256, 0, g_ctx.main>>>(buf, footprint_bytes / 4, n_ops, g_ctx.d_scratch + 7);
+        else k_probe_random<1><<<grid, 256, 0, g_ctx.main>>>(buf, footprint_bytes / 4, n_ops, g_ctx.d_scratch + 7);
+        ++g_launches;
+        cudaEventRecord(b, g_ctx.main);
+        float ms = 0;
+        if (cudaEventSynchronize(b) != cudaSuccess || cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { best = -1; break; }
+        if (rep && ms > 0) best = std::max(best, (double)n_ops / (ms * 1e-3));
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(buf);
+    if (best <= 0) { fail("gt_probe_random: %s", cudaGetErrorString(cudaGetLastError())); return -1.0; }
+    return best;
+}
+
+// Same as gt_median_count_at_least, reads already in HBM as ASCII (d_bases, 16-byte aligned) with device offsets
+// starting at 0; d_pass (device, uint8 per read) receives the decisions.  Everything is queued on the compute stream
+// (no host wait); d_kmer_total (device uint64, may be NULL) is incremented by the k-mers judged.
+extern "C" int gt_median_count_at_least_dev(gt_storage* st, int shifter, int K, const void* d_bases, const void* d_offsets,
+                                            uint64_t n_reads, uint64_t n_bases, uint32_t cutoff, void* d_pass, void* d_kmer_total) {
+    if (ensure_ctx()) return -1;
+    if (!st || !d_pass) return fail("gt_median_count_at_least_dev: NULL argument");
+    if (st->world > 1) return fail("gt_median_count_at_least_dev: not available on a sharded storage");
+    if (K < 1 || K > 65535) return fail("gt_median_count_at_least_dev: K=%d out of range (1..65535)", K);
+    if (n_reads >= (1ull << 32)) return fail("gt_median_count_at_least_dev: more than 2^32-1 reads in one call");
+    if (n_reads == 0) return 0;
+    if (!d_bases || !d_offsets) return fail("gt_median_count_at_least_dev: NULL device pointer");
+    if ((reinterpret_cast<uintptr_t>(d_bases) & 15) || (reinterpret_cast<uintptr_t>(d_offsets) & 7))
+        return fail("gt_median_count_at_least_dev: d_bases must be 16-byte aligned and d_offsets 8-byte aligned");
+    CU(cudaSetDevice(g_ctx.device));
+    if (st->pend && st->pend->pending_total() && pending_flush_sync(st)) return -1;
+    Slot& sl = g_ctx.slot[0];
+    cudaStream_t s = g_ctx.main;
+    if (sl.consumed_pending) {
+        CU(cudaStreamWaitEvent(s, sl.consumed, 0));
+        sl.consumed_pending = false;
+    }
+    CU(cudaStreamSynchronize(sl.stream));
+    if (g_ctx.apply) {  // the query must see every applied update
+        CU(cudaEventRecord(sl.packed, g_ctx.apply));
+        CU(cudaStreamWaitEvent(s, sl.packed, 0));
+    }
+    const uint64_t n_words = (n_bases + 31) / 32, n_words_alloc = n_words + halo_alloc_words();
+    if (sl.words.reserve(n_words_alloc * 8, s) || sl.flags.reserve(n_reads + 1, s) || sl.coarse.reserve(((n_bases >> COARSE_SHIFT) + 2) * 4, s) ||
+        sl.kcount.reserve(n_reads * 8, s) || sl.hits.reserve(n_reads * 4, s))
+        return -1;
+    const uint64_t* offs = static_cast<const uint64_t*>(d_offsets);
+    if (pack_on_device(static_cast<const uint8_t*>(d_bases), offs, n_reads, n_bases, 0, sl.words.as<uint64_t>(), n_words_alloc,
+                       sl.flags.as<uint8_t>(), sl.coarse.as<uint32_t>(), s))
+        return -1;
+    gt_batch view;
+    view.n_reads = n_reads;
+    view.n_bases = n_bases;
+    view.n_words = n_words;
+    view.n_words_alloc = n_words_alloc;
+    view.base0 = 0;
+    view.d_words = sl.words.as<uint64_t>();
+    view.d_offsets = const_cast<uint64_t*>(offs);
+    view.d_flags = sl.flags.as<uint8_t>();
+    view.d_coarse = sl.coarse.as<uint32_t>();
+    unsigned long long* d_tot = d_kmer_total ? static_cast<unsigned long long*>(d_kmer_total) : g_ctx.d_scratch + 4;
+    k_kmer_counts<<<grid_for(n_reads, 256, 16), 256, 0, s>>>(offs, n_reads, K, view.d_flags, sl.kcount.as<uint64_t>(), nullptr, d_tot); ++g_launches;
+    CU(cudaGetLastError());
+    CU(cudaMemsetAsync(sl.hits.p, 0, n_reads * 4, s));
+    WalkArgs a = make_args(view, K);
+    a.hits = sl.hits.as<uint32_t>();
+    a.cutoff = cutoff;
+    if (launch_walk_kind<OP_MEDIAN, false>(shifter, a, st->ts, s)) return -1;
+    k_median_decide<<<grid_for(n_reads, 256, 16), 256, 0, s>>>(sl.kcount.as<uint64_t>(), a.hits, n_reads, static_cast<uint8_t*>(d_pass)); ++g_launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+
 // DiginormFilter over a batch, batch-synchronous: every read of the CALL is judged
 // against the table state at the start of the call (median_count_at_least, diginorm.hh:35-68), then the kept
 // reads are inserted (filter_sequence, :111-119).  A call of one read reproduces the reference's serial filter

@@ -786,6 +786,21 @@ __global__ void __launch_bounds__(256) k_synth_bases(uint8_t* __restrict__ out, 
     }
 }
 
+// Roofline probes (harness helpers): independent random 32-bit RED.OR (WHAT = 0) or random 32-byte sector loads
+// (WHAT = 1) over a footprint of n_words 32-bit words -- the "random-sector roofline" R_rand the insert / query
+// rates are quoted against, measured in the same run on the same device.
+template <int WHAT>
+__global__ void __launch_bounds__(256) k_probe_random(uint32_t* __restrict__ buf, uint64_t n_words, uint64_t n_ops, unsigned long long* sink) {
+    unsigned long long acc = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_ops; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t z = synth_word(0x5eedull, i);
+        const uint64_t w = (uint64_t)(((unsigned __int128)z * n_words) >> 64);
+        if (WHAT == 0) atomicOr(buf + w, 1u << (z & 31));
+        else acc += __ldg(buf + (w & ~7ull));
+    }
+    if (WHAT == 1 && acc == 0x123456789abcdefull) *sink = acc;  // keeps the loads alive
+}
+
 // BitStorage::update_from (bitstorage.cc:103-137): dst |= src
 __global__ void __launch_bounds__(256) k_or_tables(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint64_t n_words) {
     for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words; w += (uint64_t)gridDim.x * blockDim.x)

@@ -144,6 +144,13 @@ int64_t gt_median_count_at_least(gt_storage* st, int shifter, int K, const char*
                                  const uint64_t* offsets, uint64_t n_reads, uint32_t cutoff,
                                  uint8_t* pass, uint8_t* status);
 
+/* gt_median_count_at_least for reads already resident in HBM (ASCII d_bases, 16-byte aligned; uint64 d_offsets starting
+ * at 0): pack + walk + decide queued on the compute stream with no host wait; d_pass (device, uint8 per read) receives
+ * the decisions, d_kmer_total (device uint64, may be NULL) is incremented by the k-mers judged.  The C2 workload's
+ * "per-read median-count query" (diginorm.hh:35-68 over dbg.hh:349-362). */
+int gt_median_count_at_least_dev(gt_storage* st, int shifter, int K, const void* d_bases, const void* d_offsets,
+                                 uint64_t n_reads, uint64_t n_bases, uint32_t cutoff, void* d_pass, void* d_kmer_total);
+
 /* DiginormFilter::Filter::filter_sequence over a batch (diginorm.hh:111-119; FilterProcessor,
  * processors.hh:389-417), batch-synchronous: every read of the call is judged against the table state
  * at the start of the call, then the reads that passed (median count below cutoff) are inserted.  A call
@@ -205,6 +212,10 @@ uint64_t gt_launch_count(void);
  * on the compute stream.  base(i) = "ACGT"[(splitmix64(seed + (i/32 + 1) * 0x9E3779B97F4A7C15) >> 2*(i%32)) & 3];
  * goetia_b200/synth.py is the numpy twin. */
 int gt_synth_bases_dev(void* d_out, uint64_t n_bases, uint64_t seed, uint64_t first_base);
+/* Harness helper: the random-access roofline of this device, measured now -- operations per second of independent
+ * random 32-bit RED.OR (what = 0; SURVEY.md section 8d's R_rand for inserts) or random 32-byte sector loads (what = 1;
+ * the query roofline) over a scratch footprint of footprint_bytes; device-timed, best of 3.  < 0 on error. */
+double gt_probe_random(int what, uint64_t footprint_bytes, uint64_t n_ops);
 /* Device timing for harnesses (the library launches on its own streams, which events of
  * another runtime's stream do not see).  gt_timer_record puts a CUDA event on the compute
  * stream (ordered after everything queued so far); gt_timer_elapsed_ms waits for both. */

@@ -1,10 +1,14 @@
-"""Parity properties at BASELINE.json's full sizes, where the CPU oracle cannot run in test time.
+"""Parity at BASELINE.json's full sizes, pinned to the compiled reference.
 
-The oracle pins the DIRECT path (k_walk: atomics straight on the tables) bit for bit at small sizes
-(tests/test_gpu_dbg.py); here the write-combined path (k_bucket + k_apply) must produce the same tables as the
-direct path on the full workloads, compared through gt_storage_checksum (a position-weighted checksum computed in
-HBM and itself pinned against the table bytes below), plus idempotence / occupancy / count properties.
+tests/golden/fullsize_golden.json holds, for every full-size workload, the position-weighted checksum of each table
+(gt_storage_checksum's definition) and n_occupied as produced by the UNMODIFIED reference (oracle/_ref) on the
+counter-based synthetic reads of goetia_b200/synth.py; tests/golden/make_fullsize_golden.py made it.  Here the same
+reads are generated on the device (gt_synth_bases_dev, same arithmetic), inserted through the write-combined path
+(k_bucket -> k_rebucket -> k_apply_win) AND through the direct path (k_walk), and both must reproduce the reference's
+checksums exactly.  The checksum itself is pinned against table bytes below.  Plus size-independent properties:
+idempotence of a second Bloom pass, occupancy, exact doubling of count-min answers, the per-read median query.
 """
+import json
 import math
 import os
 
@@ -15,21 +19,43 @@ from tests.util import Port, make_graph, synth_reads, table_checksum
 
 pytestmark = pytest.mark.gpu
 
+GOLD_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fullsize_golden.json")
 
-def device_reads(torch, n_reads, length, seed):
-    g = torch.Generator(device="cuda")
-    g.manual_seed(seed)
-    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device="cuda")
-    out = torch.empty(n_reads * length, dtype=torch.uint8, device="cuda")
-    step = 1 << 27
-    for i in range(0, out.numel(), step):
-        m = min(step, out.numel() - i)
-        out[i:i + m] = lut[torch.randint(0, 4, (m,), device="cuda", generator=g)]
+
+def golden(name):
+    with open(GOLD_PATH) as f:
+        g = json.load(f)
+    if name not in g:
+        pytest.skip("no golden entry %r yet (tests/golden/make_fullsize_golden.py %s)" % (name, name))
+    return g[name]
+
+
+def device_reads(torch, n_reads, length, seed, first_read=0):
+    """The reads the golden file was made from: counter-based stream `seed`, reads [first_read, +n_reads)."""
+    from goetia_b200 import _capi
+    L = _capi.lib()
+    out = torch.empty(n_reads * length + 16, dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
+    _capi.check(L.gt_synth_bases_dev(out.data_ptr(), n_reads * length, seed, first_read * length), "gt_synth_bases_dev")
+    L.gt_synchronize()
     return out
 
 
+def test_device_generator_equals_numpy_twin(gb):
+    import torch
+    from goetia_b200 import _capi
+    from goetia_b200.synth import synth_bases
+    L = _capi.lib()
+    for seed, first, n in [(44, 0, 100_000), (43, 123_456_789, 70_001), (46, 2**33 + 17, 4099)]:
+        d = torch.empty(n + 16, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        _capi.check(L.gt_synth_bases_dev(d.data_ptr(), n, seed, first), "gt_synth_bases_dev")
+        L.gt_synchronize()
+        assert np.array_equal(d[:n].cpu().numpy(), synth_bases(seed, first, n))
+
+
 def insert_all(torch, graph, reads, n_reads, length, per_call):
+    per_call -= per_call % 16  # the _dev entry points want 16-byte aligned base pointers
     offs = torch.arange(per_call + 1, dtype=torch.int64, device="cuda") * length
     torch.cuda.synchronize()
     total = 0
@@ -55,34 +81,45 @@ def test_checksum_is_the_checksum_of_the_bytes(gb, kind):
     ref.close()
 
 
-def paths_agree(gb, torch, kind, K, x, n_reads, length, seed, per_call):
-    """-> (graph built by the write-combined path, reads) after checking it against the direct path."""
-    sizes = gb.get_n_primes_near_x(4, x)
-    reads = device_reads(torch, n_reads, length, seed)
+def both_paths_equal_reference(gb, torch, name, per_call):
+    """-> (graph built by the write-combined path, reads, golden entry) after checking BOTH insert paths against the
+    reference's checksums."""
+    gold = golden(name)
+    kind, K, L, n_reads, seed = gold["kind"], gold["K"], gold["read_len"], gold["reads"], gold["seed"]
+    sizes = gb.get_n_primes_near_x(4, gold["x"])
+    assert [int(x) for x in sizes] == gold["tablesizes"]
+    reads = device_reads(torch, n_reads, L, seed, gold["first_read"])
     a = make_graph(gb, kind, 1, K, sizes)
-    nk = insert_all(torch, a, reads, n_reads, length, per_call)
-    assert nk == n_reads * (length - K + 1)
-    assert a.S.pending_info()["n_direct"] == 0  # really the bucket path, no overflow
-    sums = [a.S.checksum(i) for i in range(4)]
+    nk = insert_all(torch, a, reads, n_reads, L, per_call)
+    assert nk == gold["kmers"]
+    info = a.S.pending_info()
+    assert info["built"] == 1 and info["n_direct"] == 0  # really the bucket path, no overflow
+    assert [a.S.checksum(i) for i in range(4)] == gold["checksums"], "write-combined path differs from the reference"
+    assert a.n_occupied() == gold["n_occupied"]
     os.environ["GT_BUCKET"] = "0"  # direct path: k_walk, one atomic per (k-mer, table) on the tables
     try:
         b = make_graph(gb, kind, 1, K, sizes)
-        assert insert_all(torch, b, reads, n_reads, length, per_call) == nk
+        assert insert_all(torch, b, reads, n_reads, L, per_call) == nk
         assert not b.S.pending_info()["built"]
-        assert [b.S.checksum(i) for i in range(4)] == sums
-        occ_b = b.n_occupied()
+        assert [b.S.checksum(i) for i in range(4)] == gold["checksums"], "direct path differs from the reference"
     finally:
         os.environ.pop("GT_BUCKET", None)
-    assert a.n_occupied() == occ_b
     del b
-    return a, reads, sizes, sums
+    return a, reads, gold
+
+
+@pytest.mark.parametrize("name", ["c1", "c3_first_1m", "c2_first_1m"])
+def test_prefix_workloads_equal_reference(gb, name):
+    import torch
+    both_paths_equal_reference(gb, torch, name, 400_000)
 
 
 def test_c3_bitstorage_full_size(gb):
     """C3: BitStorage K=31, 4 x 8e9 bits, 50 M x 150 bp reads (6.0e9 k-mers)."""
     import torch
     n_reads, L, K = 50_000_000, 150, 31
-    g, reads, sizes, sums = paths_agree(gb, torch, 0, K, int(8e9), n_reads, L, 44, 6_000_000)
+    g, reads, gold = both_paths_equal_reference(gb, torch, "c3", 6_000_000)
+    sizes, sums = gold["tablesizes"], gold["checksums"]
     # idempotence: a second pass over the same reads leaves a Bloom table unchanged
     insert_all(torch, g, reads, n_reads, L, 6_000_000)
     assert [g.S.checksum(i) for i in range(4)] == sums
@@ -100,7 +137,7 @@ def test_c2_bytestorage_full_size(gb):
     """C2: ByteStorage K=21 count-min insert over 20 M x 150 bp reads, then the per-read median-count query."""
     import torch
     n_reads, L, K = 20_000_000, 150, 21
-    g, reads, sizes, sums = paths_agree(gb, torch, 1, K, int(4e9), n_reads, L, 43, 6_000_000)
+    g, reads, gold = both_paths_equal_reference(gb, torch, "c2", 6_000_000)
     # counters are counts: the byte sum of every table equals the k-mers inserted (nothing near saturation here)
     sample_n = 200_000
     sample = reads[:sample_n * L].cpu().numpy()
@@ -119,7 +156,7 @@ def test_c5_nibblestorage_long_reads(gb):
     """C5 shape at one GPU's share: NibbleStorage K=25, 10 kb reads (the long-sequence rolling-hash path)."""
     import torch
     n_reads, L, K = 125_000, 10_000, 25  # 1/8 of C5's 1 M reads = what one of 8 GPUs hashes
-    g, reads, sizes, sums = paths_agree(gb, torch, 2, K, int(8e9), n_reads, L, 46, 60_000)
+    g, reads, gold = both_paths_equal_reference(gb, torch, "c5_first_125k", 60_000)
     sample = reads[:20 * L].cpu().numpy()
     q = g.query_sequences(sample, np.arange(21, dtype=np.uint64) * np.uint64(L))
     assert q.size == 20 * (L - K + 1) and int(q.min()) >= 1 and int(q.max()) <= 15
