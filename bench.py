@@ -339,9 +339,14 @@ def main():
     check["n_occupied"] = n_occ
 
     # ---- e2e: host buffers through the C ABI ------------------------------------------------------
+    # The parsing-to-device pipeline's product is a pinned 2-bit packed batch (the FASTX front end's parser threads pack;
+    # north_star: "FastxParser -> pinned 2-bit buffers on CUDA streams"), so the headline e2e step is
+    # gt_insert_sequences_packed on packed pinned host buffers: 0.25 B/base + offsets + flags cross PCIe inside the timed
+    # region.  The same step from pinned ASCII (gt_insert_sequences, 1 B/base, packed on the device) rides along as e2e_ascii.
     e2e = None
-    host_b = host_o = None
+    host_b = None
     if not args.no_e2e:
+        from goetia_b200.batch import pack_reads_host
         host_b = torch.empty(total_reads * read_len, dtype=torch.uint8, pin_memory=True)
         p = 0
         for b, n in subs:
@@ -349,29 +354,51 @@ def main():
             p += n * read_len
         host_o = torch.empty(total_reads + 1, dtype=torch.int64, pin_memory=True)
         host_o.copy_(torch.arange(total_reads + 1, dtype=torch.int64) * read_len)
+        host_w = torch.zeros((total_reads * read_len + 31) // 32 + 1, dtype=torch.int64, pin_memory=True)
+        host_f = torch.zeros(total_reads, dtype=torch.uint8, pin_memory=True)
         torch.cuda.synchronize()
         hb, ho = host_b.numpy(), host_o.numpy().view(np.uint64)
+        hw, hf = host_w.numpy().view(np.uint64), host_f.numpy()
+        t0 = time.perf_counter()
+        pack_reads_host(hb, ho, 0, hw, hf)  # what the parser threads do; outside the timed region, reported below
+        pack_s = time.perf_counter() - t0
         os.environ.setdefault("GT_CHUNK_BASES", str(256 << 20))
 
-        def step_host():
+        def step_packed():
             if reset_each_step:
                 storage.reset()
-            nk = graph.insert_sequences(hb, ho, mode=gb.MODE_BLIND)  # returns the k-mer count read back from the device
+            nk = graph.insert_sequences_packed(hw, ho, hf, mode=gb.MODE_BLIND)  # the k-mer count is read back from the device
             storage.flush()
             return nk
 
-        for _ in range(min(args.warmup, 2)):
-            assert step_host() == kmers_per_step
-        L.gt_synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_host()
-        L.gt_synchronize()
-        dt = time.perf_counter() - t0
-        e2e = {"value": kmers_per_step * args.steps / dt, "unit": "k-mers/s",
-               "h2d_bytes_per_step": int(hb.nbytes + ho.nbytes), "d2h_bytes_per_step": 8,
-               "ms_per_step": dt * 1e3 / args.steps,
-               "api": "gt_insert_sequences(host ASCII, host offsets) + gt_storage_flush, pinned host memory"}
+        def step_ascii():
+            if reset_each_step:
+                storage.reset()
+            nk = graph.insert_sequences(hb, ho, mode=gb.MODE_BLIND)
+            storage.flush()
+            return nk
+
+        def timed(step, steps):
+            for _ in range(min(args.warmup, 2)):
+                assert step() == kmers_per_step
+            L.gt_synchronize()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                step()
+            L.gt_synchronize()
+            return (time.perf_counter() - t0) / steps
+
+        dt = timed(step_packed, args.steps)
+        dta = timed(step_ascii, max(1, args.steps // 2))
+        e2e = {"value": kmers_per_step / dt, "unit": "k-mers/s",
+               "h2d_bytes_per_step": int(hw.nbytes + ho.nbytes + hf.nbytes), "d2h_bytes_per_step": 8, "ms_per_step": dt * 1e3,
+               "api": "gt_insert_sequences_packed(pinned 2-bit words, offsets, flags) + gt_storage_flush",
+               "host_pack": {"seconds": pack_s, "bases_per_s": total_reads * read_len / pack_s, "threads": os.cpu_count(),
+                             "note": "gt_pack_reads_host, once, outside the timed region (the parser threads' share of the pipeline)"},
+               "e2e_ascii": {"value": kmers_per_step / dta, "ms_per_step": dta * 1e3, "h2d_bytes_per_step": int(hb.nbytes + ho.nbytes),
+                             "api": "gt_insert_sequences(pinned ASCII, offsets) + gt_storage_flush (packed on the device)"}}
+        check["e2e_tables_checksum_equal_reference"] = (None if gold is None else
+                                                        [storage.checksum(i) for i in range(n_tables)] == [int(x) for x in gold["checksums"]])
 
     # ---- roofline -----------------------------------------------------------------------------------
     peak, peak_src = measured_peak()
@@ -673,17 +700,25 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
     check = checksum_check(gold, [st.checksum(i) for i in range(n_tables)], n_occ)  # collective: the shards' sums add up
     check["n_occupied_all_ranks"] = n_occ
 
-    # e2e: pinned host reads -> H2D inside the timed region -> bucket -> exchange -> apply; wall clock, max over ranks
+    # e2e: pinned 2-bit packed host reads (the parser stage's product) -> H2D inside the timed region -> hash + bucket ->
+    # exchange -> apply; wall clock, max over ranks
     e2e = None
     if not args.no_e2e:
+        from goetia_b200.batch import pack_reads_host
+        wpr = (per_round * read_len + 31) // 32 + 8  # words per round (+ slack the kernels may read)
         hosts = []
         for b, n in subs:
-            h = torch.empty(b.numel(), dtype=torch.uint8, pin_memory=True)
-            h.copy_(b)
-            hosts.append(h)
+            hw = torch.zeros(wpr, dtype=torch.int64, pin_memory=True)
+            hf = torch.zeros(max(per_round, 1), dtype=torch.uint8, pin_memory=True)
+            if n:
+                ascii_np = b[:n * read_len].cpu().numpy()
+                pack_reads_host(ascii_np, np.arange(n + 1, dtype=np.uint64) * np.uint64(read_len), 0,
+                                hw.numpy().view(np.uint64), hf.numpy())
+            hosts.append((hw, hf))
         host_offs = torch.empty(per_round + 1, dtype=torch.int64, pin_memory=True)
         host_offs.copy_(offs)
-        dbuf = [torch.empty(per_round * read_len, dtype=torch.uint8, device=dev) for _ in range(2)]
+        dwords = [torch.zeros(wpr, dtype=torch.int64, device=dev) for _ in range(2)]
+        dflags = [torch.zeros(max(per_round, 1), dtype=torch.uint8, device=dev) for _ in range(2)]
         doff = [torch.empty(per_round + 1, dtype=torch.int64, device=dev) for _ in range(2)]
         copy_stream = torch.cuda.Stream()
         torch.cuda.synchronize()
@@ -691,33 +726,35 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
         pieces = max(1, int(os.environ.get("GT_BENCH_E2E_PIECES", "4")))
 
         def step_host():
-            # Every round travels in `pieces` H2D copies (copy stream); pack/hash/bucket of a piece (compute stream)
-            # starts as soon as it has landed, so only the first piece of a step is exposed.  The exchange and
-            # k_apply (apply stream) stay per round.  One result read-back (the k-mer count) ends the step.
+            # Every round travels in `pieces` H2D copies (copy stream); hash + bucket of a piece (compute stream) starts as
+            # soon as it has landed, so only the first piece of a step is exposed.  The exchange and the apply (apply
+            # stream) stay per round.  One result read-back (the k-mer count) ends the step.
             consumed = [None, None]
             if reset_each_step:
                 st.reset()
             with torch.cuda.stream(st.stream):
                 d_total.zero_()
-            for i, (h, (b, n)) in enumerate(zip(hosts, subs)):
-                d, do = dbuf[i & 1], doff[i & 1]
+            for i, ((hw, hf), (b, n)) in enumerate(zip(hosts, subs)):
+                dw, df, do = dwords[i & 1], dflags[i & 1], doff[i & 1]
                 with torch.cuda.stream(copy_stream):
                     if consumed[i & 1] is not None:
                         copy_stream.wait_event(consumed[i & 1])
                     do.copy_(host_offs, non_blocking=True)
-                # piece boundaries on multiples of 16 reads: the _dev entry points want 16-byte-aligned base pointers
-                per_piece = (-(-max(n, 1) // pieces) + 15) // 16 * 16
+                    df.copy_(hf, non_blocking=True)
+                # piece boundaries on multiples of 64 reads: a piece then starts on a 16-byte boundary of the packed stream whatever the read length
+                per_piece = (-(-max(n, 1) // pieces) + 63) // 64 * 64
                 for r0 in range(0, max(n, 1), per_piece):
                     r1 = min(max(n, 1), r0 + per_piece)
+                    w0, w1 = r0 * read_len // 32, (r1 * read_len + 31) // 32
                     with torch.cuda.stream(copy_stream):
-                        d[r0 * read_len:r1 * read_len].copy_(h[r0 * read_len:r1 * read_len], non_blocking=True)
+                        dw[w0:w1 + 1].copy_(hw[w0:w1 + 1], non_blocking=True)
                         ready = torch.cuda.Event()
                         ready.record(copy_stream)
                     st.stream.wait_event(ready)
                     if n:
                         # equal-length reads: the first r1-r0+1 offsets describe any piece
-                        st.bucket_sequences_dev_async(_capi.SHIFTER_CAN, K, d.data_ptr() + r0 * read_len, do.data_ptr(),
-                                                      r1 - r0, (r1 - r0) * read_len, d_total.data_ptr())
+                        st.bucket_packed_dev_async(_capi.SHIFTER_CAN, K, dw.data_ptr() + w0 * 8, w1 - w0 + 1, do.data_ptr(),
+                                                   df.data_ptr() + r0, r1 - r0, (r1 - r0) * read_len, d_total.data_ptr())
                 free = torch.cuda.Event()
                 free.record(st.stream)
                 consumed[i & 1] = free
@@ -726,7 +763,7 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
             return int(d_total.item())  # the step's result read back from the device
 
         for _ in range(min(args.warmup, 2)):
-            step_host()
+            assert step_host() == kmers_rank
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -736,10 +773,16 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         dts = float(dt.item())
+        n_occ2 = st.n_occupied()
+        e2e_ok = None if gold is None else ([st.checksum(i) for i in range(n_tables)] == [int(x) for x in gold["checksums"]]
+                                            and n_occ2 == int(gold["n_occupied"]))
+        check["e2e_tables_checksum_equal_reference"] = e2e_ok
         e2e = {"value": kmers_per_step * args.steps / dts, "unit": "k-mers/s",
-               "h2d_bytes_per_step": int(sum(h.numel() for h in hosts) + rounds * host_offs.numel() * 8) * world,
-               "d2h_bytes_per_step": 8 * rounds * world, "ms_per_step": dts * 1e3 / args.steps,
-               "api": "ShardedStorage: pinned host ASCII -> H2D in %d pieces per round -> bucket (+ exchange, transport %s) -> apply (per rank)" % (pieces, st.transport)}
+               "h2d_bytes_per_step": int(sum(hw.numel() * 8 + hf.numel() for hw, hf in hosts) + rounds * host_offs.numel() * 8) * world,
+               "d2h_bytes_per_step": 8 * world, "ms_per_step": dts * 1e3 / args.steps,
+               "api": "ShardedStorage: pinned 2-bit packed host reads (gt_pack_reads_host, outside the timed region) -> H2D in %d "
+                      "pieces per round -> gt_insert_packed_dev_async (hash + bucket, transport %s) -> exchange -> apply (per rank)"
+                      % (pieces, st.transport)}
 
     if rank == 0:
         peak, peak_src = measured_peak()

@@ -66,6 +66,11 @@ SIGNATURES = {
                                             C.c_uint64, C.c_int]),
     "gt_insert_sequences_dev_async": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64,
                                                 C.c_uint64, C.c_int, C.c_void_p]),
+    "gt_pack_reads_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]),
+    "gt_insert_sequences_packed": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                               C.c_int]),
+    "gt_insert_packed_dev_async": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                             C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]),
     "gt_storage_flush": (C.c_int, [C.c_void_p]),
     "gt_storage_pending_info": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gt_storage_apply": (C.c_int, [C.c_void_p]),

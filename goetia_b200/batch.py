@@ -52,3 +52,18 @@ class PackedBatch:
             self.close()
         except Exception:
             pass
+
+
+def pack_reads_host(bases, offsets, n_threads=0, words_out=None, flags_out=None):
+    """Validate + fold case + 2-bit pack a read batch on the host (gt_pack_reads_host): -> (words uint64, flags uint8).
+    The layout is the device's: base p of the batch at bits 2*(p%32) of word p/32, A=0 C=1 G=2 T=3; flags[r] = READ_INVALID
+    for a read holding a byte outside ACGTacgt.  No GPU is needed."""
+    import numpy as np
+    bases, offsets = _capi.as_reads(bases, offsets)
+    n = offsets.size - 1
+    n_bases = int(offsets[-1] - offsets[0]) if n else 0
+    words = np.zeros((n_bases + 31) // 32 + 1, dtype=np.uint64) if words_out is None else words_out
+    flags = np.zeros(max(n, 1), dtype=np.uint8) if flags_out is None else flags_out
+    _capi.check(_capi.load().gt_pack_reads_host(bases.ctypes.data, offsets.ctypes.data, n, words.ctypes.data, flags.ctypes.data,
+                                                int(n_threads)), "gt_pack_reads_host")
+    return words, flags

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/goetia_b200.h"
@@ -1002,6 +1003,243 @@ static int insert_sequences_dev_queue(gt_storage* st, int shifter, int K, const 
         CU(cudaGetLastError());
     }
     // n_bases bounds the k-mers of the batch without a round trip to the host
+    if (bucket_usable(st, mode, K, n_bases, n_bases)) {
+        if (bucket_insert(st, shifter, view, K, n_bases)) return -1;
+    } else if (launch_insert(st, shifter, view, K, mode, nullptr, s)) {
+        return -1;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// 2-bit packed HOST buffers: the parsing-to-device pipeline's product (north_star: "FastxParser -> pinned 2-bit
+// buffers on CUDA streams").  The packer runs on the host (parser threads), so only 0.25 B/base cross PCIe.
+// Layout = the device layout: base p of the batch at bits 2*(p%32) of u64 word p/32, A=0 C=1 G=2 T=3; a/c/g/t are
+// folded to upper case; a read holding any other byte gets flags[r] = GT_READ_INVALID (DNA_SIMPLE validation,
+// sequences/alphabets.hh:112-130, parsing/readers.hh:162-171) and its codes are unspecified.
+// ------------------------------------------------------------------------------------------
+static inline uint32_t host_pack8(uint64_t x, bool& bad) {
+    // per byte: code = ((c>>1)&3) ^ ((c>>2)&1); validity: (c & 0xDF) in {A, C, G, T}  (same arithmetic as k_pack)
+    uint64_t code = ((x >> 1) & 0x0303030303030303ull) ^ ((x >> 2) & 0x0101010101010101ull);
+    const uint64_t u = x & 0xDFDFDFDFDFDFDFDFull, L = 0x7F7F7F7F7F7F7F7Full;
+    uint64_t ok = 0;
+    for (uint64_t pat : {0x41ull, 0x43ull, 0x47ull, 0x54ull}) {
+        const uint64_t t = u ^ (pat * 0x0101010101010101ull);
+        ok |= ~(((t & L) + L) | t | L);
+    }
+    bad |= ok != 0x8080808080808080ull;
+    code = (code | (code >> 6)) & 0x000F000F000F000Full;
+    code = (code | (code >> 12)) & 0x000000FF000000FFull;
+    code = (code | (code >> 24)) & 0xFFFFull;
+    return (uint32_t)code;
+}
+
+static void host_pack_range(const char* bases, const uint64_t* offsets, uint64_t n_reads, uint64_t base0, uint64_t w_lo, uint64_t w_hi,
+                            uint64_t n_bases, uint64_t* words, uint8_t* flags) {
+    for (uint64_t w = w_lo; w < w_hi; ++w) {
+        const uint64_t p = w * 32;
+        uint64_t out = 0;
+        bool bad = false;
+        if (p + 32 <= n_bases) {
+            for (int k = 0; k < 4; ++k) {
+                uint64_t x;
+                memcpy(&x, bases + base0 + p + 8 * k, 8);
+                out |= (uint64_t)host_pack8(x, bad) << (16 * k);
+            }
+        } else {
+            for (int k = 0; k < 4; ++k) {
+                uint64_t x = 0;
+                for (int j = 0; j < 8; ++j) {
+                    const uint64_t q = p + 8 * k + j;
+                    x |= (uint64_t)(q < n_bases ? (unsigned char)bases[base0 + q] : (unsigned char)'A') << (8 * j);
+                }
+                out |= (uint64_t)host_pack8(x, bad) << (16 * k);
+            }
+        }
+        words[w] = out;
+        if (bad) {  // rare: flag every read owning an offending byte
+            for (uint64_t q = p; q < std::min(p + 32, n_bases); ++q) {
+                const unsigned char c = (unsigned char)bases[base0 + q] & 0xDF;
+                if (c != 'A' && c != 'C' && c != 'G' && c != 'T') {
+                    const uint64_t r = (uint64_t)(std::upper_bound(offsets, offsets + n_reads + 1, base0 + q) - offsets) - 1;
+                    __atomic_store_n(flags + r, (uint8_t)GT_READ_INVALID, __ATOMIC_RELAXED);
+                }
+            }
+        }
+    }
+}
+
+extern "C" int gt_pack_reads_host(const char* bases, const uint64_t* offsets, uint64_t n_reads, uint64_t* words, uint8_t* flags,
+                                  int n_threads) {
+    if (n_reads && (!bases || !offsets)) return fail("gt_pack_reads_host: NULL bases/offsets");
+    if (!words || !flags) return fail("gt_pack_reads_host: NULL output");
+    if (validate_offsets("gt_pack_reads_host", offsets, n_reads)) return -1;
+    if (n_reads == 0) return 0;
+    const uint64_t base0 = offsets[0], n_bases = offsets[n_reads] - base0, n_words = (n_bases + 31) / 32;
+    memset(flags, 0, n_reads);
+    int T = n_threads > 0 ? n_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    T = (int)std::min<uint64_t>((uint64_t)T, std::max<uint64_t>(1, n_words >> 16));
+    if (T <= 1) {
+        host_pack_range(bases, offsets, n_reads, base0, 0, n_words, n_bases, words, flags);
+        return 0;
+    }
+    std::vector<std::thread> th;
+    const uint64_t per = (n_words + T - 1) / T;
+    for (int t = 0; t < T; ++t) {
+        const uint64_t lo = std::min<uint64_t>(n_words, (uint64_t)t * per), hi = std::min<uint64_t>(n_words, lo + per);
+        th.emplace_back(host_pack_range, bases, offsets, n_reads, base0, lo, hi, n_bases, words, flags);
+    }
+    for (auto& x : th) x.join();
+    return 0;
+}
+
+// One chunk [r0, r1) of a packed host batch -> slot buffers.  The chunk's words start at the word holding its first
+// base; the bases of that word that belong to the previous read are covered by a PHANTOM read flagged invalid
+// (device offsets = [word start, offsets[r0..r1]]), so the walkers need no extra bounds test.
+static int stage_packed_chunk(Slot& sl, const uint64_t* words, const uint64_t* offsets, const uint8_t* flags, uint64_t r0, uint64_t r1,
+                              gt_batch& view) {
+    cudaStream_t s = sl.stream;
+    const uint64_t b0 = offsets[r0] - offsets[0], b1 = offsets[r1] - offsets[0];  // relative to words[0]
+    const uint64_t w0 = b0 / 32, w1 = (b1 + 31) / 32, nr = r1 - r0;
+    const uint64_t n_bases = b1 - w0 * 32, n_words = w1 - w0, n_words_alloc = n_words + halo_alloc_words();
+    if (sl.words.reserve(n_words_alloc * 8, s) || sl.offsets.reserve((nr + 2) * 8, s) || sl.flags.reserve(nr + 2, s) ||
+        sl.coarse.reserve(((n_bases >> COARSE_SHIFT) + 2) * 4, s))
+        return -1;
+    uint64_t* d_words = sl.words.as<uint64_t>();
+    uint64_t* d_off = sl.offsets.as<uint64_t>();
+    uint8_t* d_flags = sl.flags.as<uint8_t>();
+    if (n_words) CU(cudaMemcpyAsync(d_words, words + w0, n_words * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(d_words + n_words, 0, (n_words_alloc - n_words) * 8, s));
+    const uint64_t phantom_start = offsets[0] + w0 * 32;  // absolute, like the offsets that follow
+    CU(cudaMemcpyAsync(d_off, &phantom_start, 8, cudaMemcpyHostToDevice, s));  // pageable source: staged before the call returns
+    CU(cudaMemcpyAsync(d_off + 1, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(d_flags, READ_INVALID, 1, s));
+    CU(cudaMemcpyAsync(d_flags + 1, flags + r0, nr, cudaMemcpyHostToDevice, s));
+    k_coarse<<<grid_for(nr + 1, 256, 16), 256, 0, s>>>(d_off, nr + 1, phantom_start, sl.coarse.as<uint32_t>()); ++g_launches;
+    CU(cudaGetLastError());
+    view = gt_batch();
+    view.n_reads = nr + 1;
+    view.n_bases = n_bases;
+    view.n_words = n_words;
+    view.n_words_alloc = n_words_alloc;
+    view.base0 = phantom_start;
+    view.d_words = d_words;
+    view.d_offsets = d_off;
+    view.d_flags = d_flags;
+    view.d_coarse = sl.coarse.as<uint32_t>();
+    return 0;
+}
+
+// dBG::insert_sequence over a batch that the host has already validated and 2-bit packed (gt_pack_reads_host, or the
+// FASTX front end's workers).  words[0] bit 0 holds base offsets[0]; GT_MODE_BLIND / GT_MODE_FAST (no per-read outputs).
+extern "C" int64_t gt_insert_sequences_packed(gt_storage* st, int shifter, int K, const uint64_t* words, const uint64_t* offsets,
+                                               const uint8_t* flags, uint64_t n_reads, int mode) {
+    if (ensure_ctx()) return -1;
+    if (!st) return fail("gt_insert_sequences_packed: NULL storage");
+    if (K < 1 || K > 65535) return fail("gt_insert_sequences_packed: K=%d out of range (1..65535)", K);
+    if (mode != GT_MODE_BLIND && mode != GT_MODE_FAST) return fail("gt_insert_sequences_packed: GT_MODE_BLIND or GT_MODE_FAST");
+    if (n_reads == 0) return 0;
+    if (!words || !offsets || !flags) return fail("gt_insert_sequences_packed: NULL argument");
+    if (n_reads >= (1ull << 32) - 1) return fail("gt_insert_sequences_packed: too many reads in one call");
+    CU(cudaSetDevice(g_ctx.device));
+    if (mode != GT_MODE_BLIND && pending_flush_sync(st)) return -1;
+    if (offsets[n_reads] < offsets[0]) return fail("gt_insert_sequences_packed: offsets must be non-decreasing");
+    std::vector<uint64_t> cuts;
+    chunk_ranges(offsets, n_reads, cuts);
+    const uint64_t call_bases = offsets[n_reads] - offsets[0];
+    const uint64_t call_est = call_bases > n_reads * (uint64_t)(K - 1) ? call_bases - n_reads * (uint64_t)(K - 1) : 0;
+    const bool bucket_call = bucket_usable(st, mode, K, 0, call_est);
+    unsigned long long* d_tot = g_ctx.d_scratch + 3;
+    CU(cudaMemsetAsync(d_tot, 0, sizeof(unsigned long long), g_ctx.slot[0].stream));
+    CU(cudaStreamSynchronize(g_ctx.slot[0].stream));
+    bool any_bucketed = false;
+    for (size_t c = 0; c + 1 < cuts.size(); ++c) {
+        Slot& sl = g_ctx.slot[c & 1];
+        cudaStream_t s = sl.stream;
+        const uint64_t r0 = cuts[c], r1 = cuts[c + 1];
+        uint64_t chunk_kmers = 0;
+        for (uint64_t r = r0; r < r1; ++r) {
+            if (offsets[r + 1] < offsets[r]) {
+                cudaDeviceSynchronize();
+                return fail("gt_insert_sequences_packed: offsets must be non-decreasing (read %llu)", (unsigned long long)r);
+            }
+            const uint64_t len = offsets[r + 1] - offsets[r];
+            chunk_kmers += len >= (uint64_t)K ? len - (uint64_t)K + 1 : 0;
+        }
+        const bool bucketed = bucket_call && chunk_kmers <= st->pend->budget_kmers;
+        any_bucketed |= bucketed;
+        if (sl.consumed_pending) {
+            CU(cudaStreamWaitEvent(s, sl.consumed, 0));
+            sl.consumed_pending = false;
+        }
+        gt_batch view;
+        if (stage_packed_chunk(sl, words, offsets, flags, r0, r1, view)) return -1;
+        k_kmer_counts<<<grid_for(view.n_reads, 256, 16), 256, 0, s>>>(view.d_offsets, view.n_reads, K, view.d_flags, nullptr, nullptr, d_tot); ++g_launches;
+        CU(cudaGetLastError());
+        if (bucketed) {
+            CU(cudaEventRecord(sl.packed, s));
+            CU(cudaStreamWaitEvent(g_ctx.main, sl.packed, 0));
+            if (bucket_insert(st, shifter, view, K, chunk_kmers)) return -1;
+            CU(cudaEventRecord(sl.consumed, g_ctx.main));
+            sl.consumed_pending = true;
+        } else if (launch_insert(st, shifter, view, K, mode, nullptr, s)) {
+            return -1;
+        }
+    }
+    CU(cudaStreamSynchronize(g_ctx.slot[0].stream));
+    CU(cudaStreamSynchronize(g_ctx.slot[1].stream));
+    if (any_bucketed) {
+        CU(cudaStreamSynchronize(g_ctx.main));
+        g_ctx.slot[0].consumed_pending = g_ctx.slot[1].consumed_pending = false;
+    }
+    CU(cudaMemcpy(g_ctx.h_scratch + 3, d_tot, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return (int64_t)g_ctx.h_scratch[3];
+}
+
+// The same for a packed batch already resident in HBM: d_words[0] bit 0 = base 0, d_offsets (uint64, starting at 0),
+// d_flags (uint8 per read); the kernels may read up to n_words_alloc >= ceil(n_bases / 32) + 1 words (what lies
+// beyond the batch's last base is never used).  Queued on the compute stream, no host wait.
+extern "C" int gt_insert_packed_dev_async(gt_storage* st, int shifter, int K, const void* d_words, uint64_t n_words_alloc,
+                                          const void* d_offsets, const void* d_flags, uint64_t n_reads, uint64_t n_bases, int mode,
+                                          void* d_kmer_total) {
+    if (ensure_ctx()) return -1;
+    if (!st) return fail("gt_insert_packed_dev_async: NULL storage");
+    if (K < 1 || K > 65535) return fail("gt_insert_packed_dev_async: K=%d out of range (1..65535)", K);
+    if (mode != GT_MODE_BLIND && mode != GT_MODE_FAST) return fail("gt_insert_packed_dev_async: GT_MODE_BLIND or GT_MODE_FAST");
+    if (n_reads == 0) return 0;
+    if (!d_words || !d_offsets || !d_flags) return fail("gt_insert_packed_dev_async: NULL device pointer");
+    if (n_reads >= (1ull << 32)) return fail("gt_insert_packed_dev_async: too many reads in one call");
+    if ((reinterpret_cast<uintptr_t>(d_words) & 15) || (reinterpret_cast<uintptr_t>(d_offsets) & 7))
+        return fail("gt_insert_packed_dev_async: d_words must be 16-byte aligned and d_offsets 8-byte aligned");
+    if (n_words_alloc < (n_bases + 31) / 32 + 1) return fail("gt_insert_packed_dev_async: n_words_alloc too small");
+    CU(cudaSetDevice(g_ctx.device));
+    if (mode != GT_MODE_BLIND && pending_flush_sync(st)) return -1;
+    Slot& sl = g_ctx.slot[0];
+    cudaStream_t s = g_ctx.main;
+    if (sl.consumed_pending) {
+        CU(cudaStreamWaitEvent(s, sl.consumed, 0));
+        sl.consumed_pending = false;
+    }
+    CU(cudaStreamSynchronize(sl.stream));
+    if (sl.coarse.reserve(((n_bases >> COARSE_SHIFT) + 2) * 4, s)) return -1;
+    const uint64_t* offs = static_cast<const uint64_t*>(d_offsets);
+    k_coarse<<<grid_for(n_reads, 256, 16), 256, 0, s>>>(offs, n_reads, 0, sl.coarse.as<uint32_t>()); ++g_launches;
+    CU(cudaGetLastError());
+    gt_batch view;
+    view.n_reads = n_reads;
+    view.n_bases = n_bases;
+    view.n_words = (n_bases + 31) / 32;
+    view.n_words_alloc = n_words_alloc;
+    view.base0 = 0;
+    view.d_words = const_cast<uint64_t*>(static_cast<const uint64_t*>(d_words));
+    view.d_offsets = const_cast<uint64_t*>(offs);
+    view.d_flags = const_cast<uint8_t*>(static_cast<const uint8_t*>(d_flags));
+    view.d_coarse = sl.coarse.as<uint32_t>();
+    if (d_kmer_total) {
+        k_kmer_counts<<<grid_for(n_reads, 256, 16), 256, 0, s>>>(offs, n_reads, K, view.d_flags, nullptr, nullptr,
+                                                                 static_cast<unsigned long long*>(d_kmer_total)); ++g_launches;
+        CU(cudaGetLastError());
+    }
     if (bucket_usable(st, mode, K, n_bases, n_bases)) {
         if (bucket_insert(st, shifter, view, K, n_bases)) return -1;
     } else if (launch_insert(st, shifter, view, K, mode, nullptr, s)) {

@@ -185,6 +185,24 @@ class dBG:
                                                               d_offsets_ptr, n_reads, n_bases, mode, d_kmer_total_ptr),
                     "gt_insert_sequences_dev_async")
 
+    def insert_sequences_packed(self, words, offsets, flags, mode=MODE_BLIND):
+        """dBG::insert_sequence over a batch the host has already validated and 2-bit packed (goetia_b200.batch.pack_reads_host
+        or the FASTX front end): only 0.25 B/base cross PCIe.  Returns the k-mers consumed."""
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        n = offsets.size - 1
+        return int(_capi.check(_capi.lib().gt_insert_sequences_packed(self.S.handle, self.hasher.shifter_kind, self.K, words.ctypes.data,
+                                                                      offsets.ctypes.data, flags.ctypes.data, n, mode),
+                               "gt_insert_sequences_packed"))
+
+    def insert_packed_dev_async(self, d_words_ptr, n_words_alloc, d_offsets_ptr, d_flags_ptr, n_reads, n_bases, mode=MODE_BLIND,
+                                d_kmer_total_ptr=None):
+        """The same for a packed batch already resident in HBM; queued on the compute stream, no host wait."""
+        _capi.check(_capi.lib().gt_insert_packed_dev_async(self.S.handle, self.hasher.shifter_kind, self.K, d_words_ptr, n_words_alloc,
+                                                           d_offsets_ptr, d_flags_ptr, n_reads, n_bases, mode, d_kmer_total_ptr),
+                    "gt_insert_packed_dev_async")
+
     def flush(self):
         self.S.flush()
 

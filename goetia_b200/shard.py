@@ -258,6 +258,19 @@ class ShardedStorage:
             _capi.check(L.gt_insert_sequences_dev_async(self._h, shifter_kind, K, d_bases_ptr, d_offsets_ptr, n_reads, n_bases,
                                                         _capi.MODE_BLIND, d_kmer_total_ptr), "gt_insert_sequences_dev_async")
 
+    def bucket_packed_dev_async(self, shifter_kind, K, d_words_ptr, n_words_alloc, d_offsets_ptr, d_flags_ptr, n_reads, n_bases,
+                                d_kmer_total_ptr=None):
+        """Step 1 of a round for a batch that is already 2-bit packed in HBM (the host packed it, so only 0.25 B/base
+        crossed PCIe): hash + bucket, no pack kernel, no host wait."""
+        L = _capi.lib()
+        with self.torch.cuda.stream(self.stream):
+            if self._applied[self.cur] is not None:
+                self.stream.wait_event(self._applied[self.cur])
+            _capi.check(L.gt_storage_select_store(self._h, self.cur), "gt_storage_select_store")
+            _capi.check(L.gt_insert_packed_dev_async(self._h, shifter_kind, K, d_words_ptr, n_words_alloc, d_offsets_ptr, d_flags_ptr,
+                                                     n_reads, n_bases, _capi.MODE_BLIND, d_kmer_total_ptr),
+                        "gt_insert_packed_dev_async")
+
     def exchange_and_apply(self):
         """Steps 2 and 3 of a round (collective: every rank calls it once per round): exchange of
         the current set, k_apply of this rank's slices on the apply stream, switch sets."""

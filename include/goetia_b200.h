@@ -190,6 +190,25 @@ int gt_insert_sequences_dev_async(gt_storage* st, int shifter, int K, const void
                                   const void* d_offsets, uint64_t n_reads, uint64_t n_bases, int mode,
                                   void* d_kmer_total);
 
+/* ---- 2-bit packed host batches: the parsing-to-device pipeline's product --------------------------------------- */
+/* Validate + fold case + 2-bit pack a batch ON THE HOST (what the FASTX front end's parser threads do, so that only
+ * 0.25 B/base cross PCIe): words[ceil(n_bases/32)] in the device layout (base p of the batch at bits 2*(p%32) of word
+ * p/32, counted from offsets[0]; A=0 C=1 G=2 T=3), flags[n_reads] = GT_READ_INVALID for reads holding a byte outside
+ * ACGTacgt (FastxParser would skip them: parsing/readers.hh:162-171).  n_threads <= 0: all cores. */
+int gt_pack_reads_host(const char* bases, const uint64_t* offsets, uint64_t n_reads, uint64_t* words, uint8_t* flags,
+                       int n_threads);
+/* dBG::insert_sequence (dbg.hh:296-305) over a packed host batch (pinned memory makes the copies asynchronous):
+ * chunked H2D of words / offsets / flags on two streams, no pack kernel.  GT_MODE_BLIND or GT_MODE_FAST.  Returns the
+ * k-mers consumed. */
+int64_t gt_insert_sequences_packed(gt_storage* st, int shifter, int K, const uint64_t* words, const uint64_t* offsets,
+                                   const uint8_t* flags, uint64_t n_reads, int mode);
+/* The same for a packed batch already in HBM (d_words 16-byte aligned, bit 0 of word 0 = base 0; d_offsets uint64
+ * starting at 0; d_flags uint8 per read).  n_words_alloc >= ceil(n_bases/32) + 1 words must be readable.  Queued on the
+ * compute stream with no host wait; d_kmer_total (device uint64, may be NULL) is incremented by the k-mers consumed. */
+int gt_insert_packed_dev_async(gt_storage* st, int shifter, int K, const void* d_words, uint64_t n_words_alloc,
+                               const void* d_offsets, const void* d_flags, uint64_t n_reads, uint64_t n_bases, int mode,
+                               void* d_kmer_total);
+
 /* ---- write-combining of blind inserts --------------------------------------------------- */
 /* GT_MODE_BLIND inserts into tables larger than L2 are not applied one by one: each update
  * is appended to the bucket of its table slice and applied slice by slice (DESIGN.md,
