@@ -54,6 +54,10 @@ SIGNATURES = {
                                              C.c_uint32, C.c_void_p, C.c_void_p]),
     "gt_diginorm_sequences": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64,
                                           C.c_uint32, C.c_void_p, C.c_void_p]),
+    "gt_diginorm_sequences_serial": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64,
+                                                 C.c_uint32, C.c_void_p, C.c_void_p]),
+    "gt_insert_and_query_sequences": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
+                                                  C.c_void_p]),
     "gt_batch_pack": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "gt_batch_pack_dev": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
     "gt_batch_destroy": (None, [C.c_void_p]),

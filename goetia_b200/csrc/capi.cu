@@ -1962,6 +1962,171 @@ extern "C" int64_t gt_diginorm_sequences(gt_storage* st, int shifter, int K, con
     return (int64_t)g_ctx.h_scratch[3];
 }
 
+// split reads into chunks of <= lim bases (always at least one read per chunk)
+static void chunk_ranges_lim(const uint64_t* offsets, uint64_t n_reads, uint64_t lim, std::vector<uint64_t>& cuts) {
+    cuts.clear();
+    cuts.push_back(0);
+    uint64_t r = 0;
+    while (r < n_reads) {
+        const uint64_t start = offsets[r];
+        const uint64_t* it = std::upper_bound(offsets + r + 1, offsets + n_reads + 1, start + lim);
+        uint64_t r1 = (uint64_t)(it - offsets) - 1;
+        if (r1 <= r) r1 = r + 1;
+        cuts.push_back(r1);
+        r = r1;
+    }
+}
+
+// DiginormFilter::Filter::filter_sequence over a batch with the REFERENCE'S SERIAL SEMANTICS (diginorm.hh:111-119: reads
+// are judged and inserted one after the other, so a read sees every earlier kept read).  Parallel rounds that give
+// exactly that result:
+//   judge    median_count_at_least of every undecided read against the tables (which hold every read kept so far).
+//            Counts only grow, so a read that is dropped now would also be dropped in its serial turn: final.
+//   claim    every tentatively kept read claims the slots of its k-mers with its read index (minimum wins);
+//   verify   a tentative read that holds all its slots shares none with an EARLIER tentative read, so whatever
+//            those turn out to be its counts are the serial ones: it is kept and inserted now.  The others are judged
+//            again in the next round.  The first tentative read always holds its slots, so every round decides at least
+//            one read; reads of unrelated sequence are decided in the first round.
+// Same return values as gt_diginorm_sequences.
+extern "C" int64_t gt_diginorm_sequences_serial(gt_storage* st, int shifter, int K, const char* bases, const uint64_t* offsets,
+                                                 uint64_t n_reads, uint32_t cutoff, uint8_t* keep, uint64_t* n_kept) {
+    if (check_reads("gt_diginorm_sequences_serial", bases, offsets, n_reads, K)) return -1;
+    if (!st || !keep) return fail("gt_diginorm_sequences_serial: NULL argument");
+    if (st->world > 1) return fail("gt_diginorm_sequences_serial: not available on a sharded storage");
+    if (pending_flush_sync(st)) return -1;
+    if (validate_offsets("gt_diginorm_sequences_serial", offsets, n_reads)) return -1;
+    if (n_kept) *n_kept = 0;
+    if (n_reads == 0) return 0;
+    CU(cudaSetDevice(g_ctx.device));
+    // a chunk's claims (one per k-mer and table) must fit the claim map
+    const uint64_t lim = std::max<uint64_t>(1024, std::min<uint64_t>(chunk_bases(), ((1ull << exact_log2_cap()) / 2) / (uint64_t)st->n));
+    std::vector<uint64_t> cuts;
+    chunk_ranges_lim(offsets, n_reads, lim, cuts);
+    Slot& sl = g_ctx.slot[0];
+    cudaStream_t s = sl.stream;
+    CU(cudaStreamSynchronize(g_ctx.slot[1].stream));
+    unsigned long long* d_tot = g_ctx.d_scratch + 3;    // k-mers judged
+    unsigned long long* d_kept = g_ctx.d_scratch + 5;   // reads kept
+    unsigned long long* d_tent = g_ctx.d_scratch + 4;   // tentative keeps of a round
+    CU(cudaMemsetAsync(d_tot, 0, 8, s));
+    CU(cudaMemsetAsync(d_kept, 0, 8, s));
+    for (size_t c = 0; c + 1 < cuts.size(); ++c) {
+        const uint64_t r0 = cuts[c], r1 = cuts[c + 1], nr = r1 - r0;
+        gt_batch view;
+        if (stage_chunk(sl, bases, offsets, r0, r1, view)) return -1;
+        // out8: [state | flags of the round | conflict | keep]
+        if (sl.kcount.reserve(nr * 8, s) || sl.hits.reserve(nr * 4, s) || sl.out8.reserve(4 * nr, s)) return -1;
+        uint8_t* d_state = sl.out8.as<uint8_t>();
+        uint8_t* d_rflags = d_state + nr;
+        uint8_t* d_conf = d_state + 2 * nr;
+        uint8_t* d_keep = d_state + 3 * nr;
+        const int g = grid_for(nr, 256, 16);
+        k_kmer_counts<<<g, 256, 0, s>>>(view.d_offsets, nr, K, view.d_flags, sl.kcount.as<uint64_t>(), nullptr, d_tot); ++g_launches;
+        CU(cudaGetLastError());
+        CU(cudaMemsetAsync(d_state, RD_UNDECIDED, nr, s));
+        gt_batch sub = view;
+        sub.d_flags = d_rflags;
+        for (uint64_t round = 0;; ++round) {
+            k_rd_select<<<g, 256, 0, s>>>(d_state, view.d_flags, nr, RD_UNDECIDED, d_rflags); ++g_launches;
+            CU(cudaMemsetAsync(sl.hits.p, 0, nr * 4, s));
+            WalkArgs a = make_args(sub, K);
+            a.hits = sl.hits.as<uint32_t>();
+            a.cutoff = cutoff;
+            if (launch_walk_kind<OP_MEDIAN, false>(shifter, a, st->ts, s)) return -1;
+            CU(cudaMemsetAsync(d_tent, 0, 8, s));
+            k_rd_judge<<<g, 256, 0, s>>>(sl.kcount.as<uint64_t>(), a.hits, nr, d_state, d_tent); ++g_launches;
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(g_ctx.h_scratch + 4, d_tent, 8, cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));
+            if (g_ctx.h_scratch[4] == 0) break;
+            k_rd_select<<<g, 256, 0, s>>>(d_state, view.d_flags, nr, RD_TENTATIVE, d_rflags); ++g_launches;
+            WalkArgs b = make_args(sub, K);
+            if (exact_map(view.n_bases * (uint64_t)st->n, s, b.claims)) return -1;
+            if (launch_walk_kind<OP_RD_CLAIM, false>(shifter, b, st->ts, s)) return -1;
+            CU(cudaMemsetAsync(d_conf, 0, nr, s));
+            b.conflict = d_conf;
+            if (launch_walk_kind<OP_RD_VERIFY, false>(shifter, b, st->ts, s)) return -1;
+            k_rd_settle<<<g, 256, 0, s>>>(d_conf, nr, d_state); ++g_launches;
+            k_rd_select<<<g, 256, 0, s>>>(d_state, view.d_flags, nr, RD_KEEP_NOW, d_rflags); ++g_launches;
+            CU(cudaGetLastError());
+            if (launch_insert(st, shifter, sub, K, GT_MODE_BLIND, nullptr, s)) return -1;
+            k_rd_finish<<<g, 256, 0, s>>>(nr, d_state, d_keep, d_kept, 0); ++g_launches;
+            CU(cudaGetLastError());
+        }
+        k_rd_finish<<<g, 256, 0, s>>>(nr, d_state, d_keep, d_kept, 1); ++g_launches;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(keep + r0, d_keep, nr, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    CU(cudaMemcpy(g_ctx.h_scratch + 3, d_tot, 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(g_ctx.h_scratch + 5, d_kept, 8, cudaMemcpyDeviceToHost));
+    if (n_kept) *n_kept = g_ctx.h_scratch[5];
+    return (int64_t)g_ctx.h_scratch[3];
+}
+
+// dBG::insert_and_query_sequence over a batch (dbg.hh:327-340; the input of StreamingSolidFilter, solidifier.hh:58-76):
+// every k-mer is inserted and its count AFTER its own insert is returned -- with the reference's serial semantics over
+// the whole batch (reads in order, k-mers left to right): kernels.cuh, "Batched serial insert_and_query".  counts are
+// laid out like gt_query_sequences.  BitStorage::insert_and_query is always 1 (bitstorage.cc:78-84).
+extern "C" int64_t gt_insert_and_query_sequences(gt_storage* st, int shifter, int K, const char* bases, const uint64_t* offsets,
+                                                  uint64_t n_reads, int16_t* counts, uint8_t* status) {
+    if (check_reads("gt_insert_and_query_sequences", bases, offsets, n_reads, K)) return -1;
+    if (!st || !counts) return fail("gt_insert_and_query_sequences: NULL argument");
+    if (st->world > 1) return fail("gt_insert_and_query_sequences: not available on a sharded storage");
+    if (pending_flush_sync(st)) return -1;
+    if (validate_offsets("gt_insert_and_query_sequences", offsets, n_reads)) return -1;
+    if (n_reads == 0) return 0;
+    CU(cudaSetDevice(g_ctx.device));
+    std::vector<uint64_t> cuts;
+    chunk_ranges(offsets, n_reads, cuts);
+    Slot& sl = g_ctx.slot[0];
+    cudaStream_t s = sl.stream;
+    CU(cudaStreamSynchronize(g_ctx.slot[1].stream));
+    unsigned long long* d_left = g_ctx.d_scratch + 4;
+    int64_t total = 0;
+    for (size_t c = 0; c + 1 < cuts.size(); ++c) {
+        const uint64_t r0 = cuts[c], r1 = cuts[c + 1], nr = r1 - r0;
+        gt_batch view;
+        if (stage_chunk(sl, bases, offsets, r0, r1, view)) return -1;
+        if (sl.kcount.reserve(nr * 8, s) || sl.koff.reserve(nr * 8, s) || sl.out8.reserve(nr, s)) return -1;
+        const int64_t nk = batch_kmers(view, K, sl.kcount.as<uint64_t>(), sl.out8.as<uint8_t>(), s);
+        if (nk < 0) return -1;
+        if (scan_counts(sl, sl.kcount.as<uint64_t>(), nr, sl.koff.as<uint64_t>(), s)) return -1;
+        if (sl.out16.reserve((uint64_t)nk * 2 + 2, s)) return -1;
+        if (sl.nmask.reserve(view.n_bases + 16, s)) return -1;  // done[] per position
+        uint8_t* d_done = sl.nmask.as<uint8_t>();
+        CU(cudaMemsetAsync(d_done, 0, view.n_bases + 1, s));
+        WalkArgs a = make_args(view, K);
+        a.koff = sl.koff.as<uint64_t>();
+        a.counts = sl.out16.as<int16_t>();
+        a.done = d_done;
+        a.n_left = d_left;
+        const uint64_t n_tiles = (view.n_bases + TILE_POS - 1) / TILE_POS;
+        const uint64_t per = std::max<uint64_t>(1, ((1ull << exact_log2_cap()) / 2) / ((uint64_t)TILE_POS * st->n));
+        if (direct_begin(st, s)) return -1;
+        for (uint64_t t0 = 0; t0 < n_tiles; t0 += per) {  // groups of tiles in serial order, each run to completion
+            a.tile_lo = t0;
+            a.tile_n = std::min(per, n_tiles - t0);
+            const uint64_t positions = std::min<uint64_t>(a.tile_n * TILE_POS, view.n_bases - t0 * TILE_POS);
+            for (uint64_t round = 0;; ++round) {
+                if (exact_map(positions * st->n, s, a.claims)) return -1;
+                if (launch_walk_kind<OP_IQ_CLAIM, false>(shifter, a, st->ts, s)) return -1;
+                CU(cudaMemsetAsync(d_left, 0, 8, s));
+                if (launch_walk_kind<OP_IQ_APPLY, false>(shifter, a, st->ts, s)) return -1;
+                CU(cudaMemcpyAsync(g_ctx.h_scratch + 4, d_left, 8, cudaMemcpyDeviceToHost, s));
+                CU(cudaStreamSynchronize(s));
+                if (g_ctx.h_scratch[4] == 0) break;
+            }
+        }
+        if (direct_end(st, s)) return -1;
+        if (nk) CU(cudaMemcpyAsync(counts + total, a.counts, (uint64_t)nk * 2, cudaMemcpyDeviceToHost, s));
+        if (status) CU(cudaMemcpyAsync(status + r0, sl.out8.p, nr, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        total += nk;
+    }
+    return total;
+}
+
 // ------------------------------------------------------------------------------------------
 // hash-vector members
 // ------------------------------------------------------------------------------------------

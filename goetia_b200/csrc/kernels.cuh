@@ -238,6 +238,54 @@ __device__ __forceinline__ bool storage_insert_exact(const TableSet& ts, const C
 }
 
 // ------------------------------------------------------------------------------------------
+// Batched serial insert_and_query (dbg.hh:327-340 over Storage::insert_and_query, bytestorage.cc:142-150,
+// nibblestorage.cc:102-109).  The reference inserts k-mers one at a time and returns each k-mer's count AFTER its own
+// insert, so k-mer j sees every earlier k-mer of the batch that shares one of its slots (SURVEY.md section 8a:
+// count_j = min_i min(max, pre_i + rank_j(i, bin) + 1)).  Rounds reproduce that for any thread interleaving: in a round
+// every unprocessed k-mer posts its position as a claim on each of its slots (the map keeps the minimum); a k-mer that
+// holds ALL its slots has no unprocessed predecessor on any of them, so the tables show exactly the serial state it
+// would see: it reads its counts, increments, and is done.  The smallest unprocessed position always wins, so every
+// round makes progress; the number of rounds is the largest multiplicity of a slot within the batch.
+// ------------------------------------------------------------------------------------------
+template <int KIND, int NT>
+__device__ __forceinline__ void storage_claim_always(const TableSet& ts, const ClaimMap& m, uint64_t h, uint32_t ord) {
+    const int nt = NT > 0 ? NT : ts.n;
+#pragma unroll
+    for (int i = 0; i < nt; ++i) claim_post(m, claim_key(i, fastmod_u64(h, ts.size[i], ts.magic[i])), ord);
+}
+template <int KIND, int NT>
+__device__ __forceinline__ bool storage_holds_all(const TableSet& ts, const ClaimMap& m, uint64_t h, uint32_t ord) {
+    const int nt = NT > 0 ? NT : ts.n;
+    bool all = true;
+#pragma unroll
+    for (int i = 0; i < nt; ++i) all &= claim_winner(m, claim_key(i, fastmod_u64(h, ts.size[i], ts.magic[i]))) == ord;
+    return all;
+}
+// Storage::insert_and_query of a k-mer that holds all its slots this round: the count after its own insert
+template <int KIND, int NT>
+__device__ __forceinline__ uint32_t storage_insert_and_query(const TableSet& ts, uint64_t h) {
+    const int nt = NT > 0 ? NT : ts.n;
+    constexpr uint32_t fmax = KIND == 0 ? 1u : KIND == 1 ? 255u : 15u;
+    uint32_t acc = fmax;
+#pragma unroll
+    for (int i = 0; i < nt; ++i) {
+        const uint64_t bin = fastmod_u64(h, ts.size[i], ts.magic[i]);
+        // the slot is this k-mer's alone in this round; neighbours in the same word may change, hence the atomic update
+        uint32_t v;
+        if constexpr (KIND == 0) v = 1u;
+        else if constexpr (KIND == 1) v = __ldcg(reinterpret_cast<const uint8_t*>(ts.ptr[i]) + bin);
+        else {
+            const uint32_t b = __ldcg(reinterpret_cast<const uint8_t*>(ts.ptr[i]) + (bin >> 1));
+            v = (bin & 1) ? (b & 15u) : (b >> 4);
+        }
+        if constexpr (KIND != 0) v = min(fmax, v + 1u);
+        acc = min(acc, v);
+        slot_insert<KIND, false>(ts.ptr[i], bin);
+    }
+    return acc;
+}
+
+// ------------------------------------------------------------------------------------------
 // K0: validate + 2-bit pack.  One thread per output word (32 bases = 2 x 16 B loads).
 // Folds a/c/g/t to upper case exactly as DNA_SIMPLE::_validate (sequences/alphabets.hh:112-130);
 // any other byte flags its read GT_READ_INVALID (the parser would skip it:
@@ -441,7 +489,10 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_final(const uint64_t* __res
 // OP: 0 insert, 1 query -> counts, 2 hash -> fw/rc out, 3 median hits (count >= cutoff per read),
 //     4 / 5 the two passes of GT_MODE_EXACT over the tiles [tile_lo, tile_lo + tile_n)
 // ------------------------------------------------------------------------------------------
-enum { OP_INSERT = 0, OP_QUERY = 1, OP_HASH = 2, OP_MEDIAN = 3, OP_CLAIM = 4, OP_INSERT_EXACT = 5 };
+//     6 / 7 the claim / apply rounds of the batched serial insert_and_query (see k_walk), 8 / 9 the claim / verify
+//     passes of the serial-equivalent diginorm (read-level conflicts)
+enum { OP_INSERT = 0, OP_QUERY = 1, OP_HASH = 2, OP_MEDIAN = 3, OP_CLAIM = 4, OP_INSERT_EXACT = 5,
+       OP_IQ_CLAIM = 6, OP_IQ_APPLY = 7, OP_RD_CLAIM = 8, OP_RD_VERIFY = 9 };
 
 struct WalkArgs {
     const uint64_t* words;     // packed bases
@@ -465,6 +516,11 @@ struct WalkArgs {
     // GT_MODE_EXACT: tile range of this launch (tile_n == 0: all tiles); ordinal = position - tile_lo * TILE_POS
     uint64_t tile_lo, tile_n;
     ClaimMap claims;
+    // OP_IQ_*: done[p] = 1 once the k-mer at position p has been inserted-and-queried; n_left counts the k-mers a round
+    // had to leave for the next one.  OP_RD_VERIFY: conflict[r] = 1 when read r shares a slot with an earlier claimed read.
+    uint8_t* done;
+    uint8_t* conflict;
+    unsigned long long* n_left;
 };
 
 template <int OP, int KIND, bool CAN, bool TRACK, int NT>
@@ -486,6 +542,7 @@ k_walk(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts) 
     if (a.tile_n && a.tile_lo + a.tile_n < n_tiles) n_tiles = a.tile_lo + a.tile_n;
     unsigned long long block_new = 0;
     constexpr bool COUNT_NEW = (OP == OP_INSERT && TRACK) || OP == OP_INSERT_EXACT;
+    constexpr bool COUNT_LEFT = OP == OP_IQ_APPLY;
 
     for (uint64_t tile = a.tile_lo + blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         __syncthreads();  // previous tile's smem fully consumed (and tab visible)
@@ -578,6 +635,21 @@ k_walk(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts) 
                     } else if constexpr (OP == OP_INSERT_EXACT) {
                         bool nw = storage_insert_exact<KIND, NT>(ts, a.claims, h, (uint32_t)(p - a.tile_lo * TILE_POS));
                         acc += nw, block_new += nw;
+                    } else if constexpr (OP == OP_IQ_CLAIM) {
+                        if (!a.done[p]) storage_claim_always<KIND, NT>(ts, a.claims, h, (uint32_t)p);
+                    } else if constexpr (OP == OP_IQ_APPLY) {
+                        if (!a.done[p]) {
+                            if (storage_holds_all<KIND, NT>(ts, a.claims, h, (uint32_t)p)) {
+                                a.counts[a.koff[r] + (p - rstart)] = (int16_t)storage_insert_and_query<KIND, NT>(ts, h);
+                                a.done[p] = 1;
+                            } else {
+                                ++block_new;  // left for the next round
+                            }
+                        }
+                    } else if constexpr (OP == OP_RD_CLAIM) {
+                        storage_claim_always<KIND, NT>(ts, a.claims, h, (uint32_t)r);
+                    } else if constexpr (OP == OP_RD_VERIFY) {
+                        if (!storage_holds_all<KIND, NT>(ts, a.claims, h, (uint32_t)r)) a.conflict[r] = 1;
                     } else if constexpr (OP == OP_QUERY) {
                         a.counts[a.koff[r] + (p - rstart)] = (int16_t)storage_query<KIND, NT>(ts, h);
                     } else if constexpr (OP == OP_HASH) {
@@ -595,9 +667,9 @@ k_walk(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts) 
             }
         }
     }
-    if constexpr (COUNT_NEW) {
+    if constexpr (COUNT_NEW || COUNT_LEFT) {
         for (int o = 16; o; o >>= 1) block_new += __shfl_down_sync(0xffffffffu, block_new, o);
-        if ((tid & 31) == 0 && block_new) atomicAdd(a.n_unique, block_new);
+        if ((tid & 31) == 0 && block_new) atomicAdd(COUNT_LEFT ? a.n_left : a.n_unique, block_new);
     }
 }
 
@@ -630,6 +702,51 @@ __global__ void __launch_bounds__(256) k_diginorm_keep(const uint64_t* __restric
     }
     for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_kept, mine);
+}
+
+// Serial-equivalent diginorm (capi.cu, gt_diginorm_sequences_serial): per-read state machine helpers.
+//   state: 0 undecided, 1 kept (inserted), 2 dropped, 3 tentative keep of this round, 4 kept in this round (to insert)
+enum { RD_UNDECIDED = 0, RD_KEPT = 1, RD_DROPPED = 2, RD_TENTATIVE = 3, RD_KEEP_NOW = 4 };
+// flags_out[r] = 0 for the reads in state `want` (and valid), READ_INVALID otherwise: the walkers then see only those reads
+__global__ void __launch_bounds__(256) k_rd_select(const uint8_t* __restrict__ state, const uint8_t* __restrict__ flags, uint64_t n_reads,
+                                                    uint8_t want, uint8_t* __restrict__ flags_out) {
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n_reads; r += (uint64_t)gridDim.x * blockDim.x)
+        flags_out[r] = (state[r] == want && !(flags[r] & READ_INVALID)) ? 0 : READ_INVALID;
+}
+// after the median walk over the undecided reads: dropped (final: counts only grow) or tentative keep
+__global__ void __launch_bounds__(256) k_rd_judge(const uint64_t* __restrict__ kcount, const uint32_t* __restrict__ hits, uint64_t n_reads,
+                                                   uint8_t* __restrict__ state, unsigned long long* __restrict__ n_tentative) {
+    unsigned long long mine = 0;
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n_reads; r += (uint64_t)gridDim.x * blockDim.x) {
+        if (state[r] != RD_UNDECIDED) continue;
+        const uint64_t n = kcount[r];
+        const unsigned min_req = (unsigned)(0.5 + (double)((float)n / 2.0f));
+        const bool keep = n > 0 && hits[r] < min_req;
+        state[r] = keep ? RD_TENTATIVE : RD_DROPPED;
+        mine += keep;
+    }
+    for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_tentative, mine);
+}
+// after the verify walk: a tentative read without a conflict is kept now; the others are judged again next round
+__global__ void __launch_bounds__(256) k_rd_settle(const uint8_t* __restrict__ conflict, uint64_t n_reads, uint8_t* __restrict__ state) {
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n_reads; r += (uint64_t)gridDim.x * blockDim.x)
+        if (state[r] == RD_TENTATIVE) state[r] = conflict[r] ? RD_UNDECIDED : RD_KEEP_NOW;
+}
+__global__ void __launch_bounds__(256) k_rd_finish(uint64_t n_reads, uint8_t* __restrict__ state, uint8_t* __restrict__ keep,
+                                                    unsigned long long* __restrict__ n_kept, int final_pass) {
+    unsigned long long mine = 0;
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n_reads; r += (uint64_t)gridDim.x * blockDim.x) {
+        if (state[r] == RD_KEEP_NOW) state[r] = RD_KEPT;
+        if (final_pass) {
+            keep[r] = state[r] == RD_KEPT ? 1 : 0;
+            mine += state[r] == RD_KEPT;
+        }
+    }
+    if (final_pass) {
+        for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+        if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_kept, mine);
+    }
 }
 
 __global__ void __launch_bounds__(256) k_flag_unkept(const uint8_t* __restrict__ keep, uint64_t n_reads, uint8_t* __restrict__ flags) {

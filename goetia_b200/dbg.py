@@ -311,11 +311,29 @@ class dBG:
             raise InvalidCharacterException("sequence holds a non-ACGT character")
         return [int(c) for c in counts]
 
+    def insert_and_query_sequences(self, bases, offsets, want_status=False):
+        """dBG::insert_and_query_sequence over a read batch with the reference's serial semantics (each k-mer's count is
+        the one AFTER its own insert and sees every earlier k-mer of the batch): one call, a few kernel rounds
+        (gt_insert_and_query_sequences).  counts are laid out like query_sequences."""
+        L = _capi.lib()
+        bases, offsets = _capi.as_reads(bases, offsets)
+        n = offsets.size - 1
+        lens = (offsets[1:] - offsets[:-1]).astype(np.int64)
+        cap = int(np.maximum(lens - self.K + 1, 0).sum())
+        counts = np.zeros(max(cap, 1), dtype=np.int16)
+        status = np.zeros(max(n, 1), dtype=np.uint8)
+        tot = _capi.check(L.gt_insert_and_query_sequences(self.S.handle, self.hasher.shifter_kind, self.K, bases.ctypes.data,
+                                                          offsets.ctypes.data, n, counts.ctypes.data, status.ctypes.data),
+                          "gt_insert_and_query_sequences")
+        return (counts[:tot], status[:n]) if want_status else counts[:tot]
+
     def insert_and_query_sequence(self, sequence):
-        """dbg.hh:327-340.  Serial semantics (each k-mer sees the earlier k-mers of the same
-        sequence), so the k-mers are issued one launch at a time; not a throughput path."""
-        hs = self.hasher.hashes(sequence if isinstance(sequence, str) else sequence.decode("ascii"))
-        return [self.S.insert_and_query(h.value()) for h in hs]
+        """dbg.hh:327-340: the counts after insertion, each k-mer seeing the earlier k-mers of the same sequence."""
+        bases, offsets = self._one(sequence)
+        counts, status = self.insert_and_query_sequences(bases, offsets, want_status=True)
+        if status[0] & _capi.READ_INVALID:
+            raise InvalidCharacterException("sequence holds a non-ACGT character")
+        return [int(c) for c in counts]
 
     def get_kmer_counts(self, sequence):
         return self.query_sequence(sequence)

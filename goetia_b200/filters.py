@@ -1,10 +1,12 @@
-"""Read filters on the GPU dBG: DiginormFilter (include/goetia/diginorm.hh:25-125) and its
-FilterProcessor (include/goetia/processors.hh:347-430).
+"""Read filters on the GPU dBG: DiginormFilter (include/goetia/diginorm.hh:25-125), StreamingSolidFilter
+(include/goetia/solidifier.hh:33-77) and their FilterProcessor (include/goetia/processors.hh:347-430).
 
-The reference judges and inserts one read at a time.  Here a whole batch is judged against the table
-state at the start of the batch and the passing reads are then inserted (the *batch-synchronous* rule,
-SURVEY.md section 8a); ``batch_reads=1`` reproduces the reference exactly; the parity tests run the CPU
-checker with the same batch size.
+The reference judges and inserts one read at a time.  By DEFAULT the filters here give exactly that result for a whole
+batch: DiginormFilter through gt_diginorm_sequences_serial (rounds of judge / claim / verify / insert that decide what
+the serial loop decides), StreamingSolidFilter through gt_insert_and_query_sequences (the serial post-insert counts of
+every k-mer of the batch).  ``DiginormFilter(..., batch_synchronous=True)`` opts into the one-round approximation
+(every read of a batch judged against the table state at the start of the batch -- SURVEY.md section 8a): faster, but
+redundancy INSIDE a batch is not removed, so its output differs from the reference's.
 """
 import ctypes as C
 
@@ -17,12 +19,13 @@ from .parsing import FastxParser
 class DiginormFilter:
     """``DiginormFilter[dBG].Filter``: ``build(graph, cutoff)``, ``filter_sequence``."""
 
-    def __init__(self, graph, cutoff):
+    def __init__(self, graph, cutoff, batch_synchronous=False):
         self.graph, self.K, self.cutoff = graph, graph.K, int(cutoff)
+        self.batch_synchronous = bool(batch_synchronous)
 
     @classmethod
-    def build(cls, graph, cutoff):
-        return cls(graph, cutoff)
+    def build(cls, graph, cutoff, batch_synchronous=False):
+        return cls(graph, cutoff, batch_synchronous)
 
     @staticmethod
     def median_count_at_least(sequence, cutoff, graph):
@@ -31,15 +34,17 @@ class DiginormFilter:
         return bool(graph.median_count_at_least(bases, offsets, cutoff)[0])
 
     def filter_sequences(self, bases, offsets):
-        """One batch: (keep uint8[n_reads], k-mers judged).  Kept reads have been inserted."""
+        """One batch: (keep uint8[n_reads], k-mers judged).  Kept reads have been inserted.  Serial semantics (the
+        reference's) unless the filter was built with batch_synchronous=True."""
         L = _capi.lib()
         bases, offsets = _capi.as_reads(bases, offsets)
         n = offsets.size - 1
         keep = np.zeros(max(n, 1), dtype=np.uint8)
         n_kept = C.c_uint64(0)
-        nk = _capi.check(L.gt_diginorm_sequences(self.graph.S.handle, self.graph.hasher.shifter_kind, self.K,
-                                                 bases.ctypes.data, offsets.ctypes.data, n, self.cutoff,
-                                                 keep.ctypes.data, C.byref(n_kept)), "gt_diginorm_sequences")
+        fn, name = ((L.gt_diginorm_sequences, "gt_diginorm_sequences") if self.batch_synchronous
+                    else (L.gt_diginorm_sequences_serial, "gt_diginorm_sequences_serial"))
+        nk = _capi.check(fn(self.graph.S.handle, self.graph.hasher.shifter_kind, self.K, bases.ctypes.data, offsets.ctypes.data, n,
+                            self.cutoff, keep.ctypes.data, C.byref(n_kept)), name)
         return keep[:n], int(nk)
 
     def filter_sequence(self, sequence):
@@ -53,10 +58,10 @@ class DiginormFilter:
 
 
 class StreamingSolidFilter:
-    """``StreamingSolidFilter[dBG].Filter`` (include/goetia/solidifier.hh:33-77): a read passes when fewer than
-    ``1 - min_prop_solid`` of its k-mers have an insert_and_query count below ``solid_threshold``.  The counts are
-    the reference's serial ones (each k-mer sees the earlier k-mers of the read: dbg.hh:327-340), so this filter
-    runs on the per-k-mer latency path; it is here for API completeness, not throughput."""
+    """``StreamingSolidFilter[dBG].Filter`` (include/goetia/solidifier.hh:33-77): every read is inserted; it passes when
+    fewer than ``1 - min_prop_solid`` of its k-mers have an insert_and_query count below ``solid_threshold``.  The counts are
+    the reference's serial ones (each k-mer sees every earlier k-mer: dbg.hh:327-340), produced for a whole batch by
+    gt_insert_and_query_sequences."""
 
     def __init__(self, graph, min_prop_solid=0.75, solid_threshold=1):
         self.graph, self.K = graph, graph.K
@@ -66,33 +71,32 @@ class StreamingSolidFilter:
     def build(cls, graph, min_prop_solid=0.75, solid_threshold=1):
         return cls(graph, min_prop_solid, solid_threshold)
 
+    def _decide(self, n_not_solid, n_kmers):
+        # arithmetic as the reference writes it (solidifier.hh:68): a float quotient against a double difference
+        # whose subtrahend is the float member min_prop_solid
+        return not (float(np.float32(n_not_solid) / np.float32(n_kmers)) >= 1.0 - float(np.float32(self.min_prop_solid)))
+
     def filter_sequence(self, sequence):
         counts = self.graph.insert_and_query_sequence(sequence)
         n_kmers = len(sequence) - self.K + 1
         n_not_solid = sum(1 for c in counts if c < self.solid_threshold)
-        # arithmetic as the reference writes it (solidifier.hh:68): a float quotient against a double difference
-        # whose subtrahend is the float member min_prop_solid
-        if float(np.float32(n_not_solid) / np.float32(n_kmers)) >= 1.0 - float(np.float32(self.min_prop_solid)):
-            return False, n_kmers
-        return True, n_kmers
+        return self._decide(n_not_solid, n_kmers), n_kmers
 
     def filter_sequences(self, bases, offsets):
-        """Reads one after the other (the serial semantics do not batch); -> (keep, k-mers judged)."""
+        """One batch, one library call: -> (keep uint8[n_reads], k-mers judged).  Reads shorter than K or holding a
+        foreign symbol are skipped, as the processor swallows their exceptions (processors.hh:395-403)."""
         bases, offsets = _capi.as_reads(bases, offsets)
         n = offsets.size - 1
+        counts, status = self.graph.insert_and_query_sequences(bases, offsets, want_status=True)
+        lens = (offsets[1:] - offsets[:-1]).astype(np.int64)
+        nk = np.where(status == 0, np.maximum(lens - self.K + 1, 0), 0)
+        ends = np.cumsum(nk)
+        not_solid = np.concatenate([[0], np.cumsum(counts < self.solid_threshold)])
         keep = np.zeros(n, dtype=np.uint8)
-        judged = 0
-        for r in range(n):
-            seq = bases[int(offsets[r]):int(offsets[r + 1])].tobytes().decode("ascii")
-            if len(seq) < self.K:
-                continue  # SequenceLengthException, swallowed by the processor (processors.hh:395-403)
-            try:
-                ok, nk = self.filter_sequence(seq)
-            except ValueError:
-                continue  # InvalidCharacterException, swallowed likewise
-            keep[r] = 1 if ok else 0
-            judged += nk
-        return keep, judged
+        for r in np.nonzero(nk > 0)[0]:
+            e = int(ends[r])
+            keep[r] = 1 if self._decide(int(not_solid[e] - not_solid[e - int(nk[r])]), int(nk[r])) else 0
+        return keep, int(nk.sum())
 
 
 class FilterProcessor:

@@ -160,6 +160,20 @@ int64_t gt_diginorm_sequences(gt_storage* st, int shifter, int K, const char* ba
                               const uint64_t* offsets, uint64_t n_reads, uint32_t cutoff, uint8_t* keep,
                               uint64_t* n_kept);
 
+/* The same filter with the REFERENCE'S SERIAL semantics (diginorm.hh:111-119 judges and inserts read by read, so a read
+ * sees every earlier kept read of the batch): rounds of judge / claim / verify / insert that decide, in parallel, exactly
+ * what the one-at-a-time loop decides (see capi.cu).  Same arguments and return values.  This is what FilterProcessor
+ * uses by default; gt_diginorm_sequences (batch-synchronous, one round) is the faster opt-in. */
+int64_t gt_diginorm_sequences_serial(gt_storage* st, int shifter, int K, const char* bases,
+                                     const uint64_t* offsets, uint64_t n_reads, uint32_t cutoff, uint8_t* keep,
+                                     uint64_t* n_kept);
+/* dBG::insert_and_query_sequence over a batch (dbg.hh:327-340; StreamingSolidFilter's input, solidifier.hh:58-76): every
+ * k-mer is inserted and its count AFTER its own insert returned (Storage::insert_and_query: bitstorage.cc:78-84 always 1;
+ * bytestorage.cc:142-150, nibblestorage.cc:102-109), with the serial semantics of the reference over the whole batch --
+ * count_j = min_i min(max, pre_i + rank_j(i, bin) + 1), SURVEY.md section 8a.  counts laid out like gt_query_sequences. */
+int64_t gt_insert_and_query_sequences(gt_storage* st, int shifter, int K, const char* bases,
+                                      const uint64_t* offsets, uint64_t n_reads, int16_t* counts, uint8_t* status);
+
 /* ---- device-resident batches (the parsing-to-device pipeline's product) --------------- */
 /* Upload + validate + 2-bit pack a batch (A=0 C=1 G=2 T=3; flat base p at bits 2*(p%32) of
  * 64-bit word p/32).  The batch stays in HBM until destroyed and can be inserted / queried
