@@ -158,6 +158,20 @@ def synth_reads_device(torch, L, first_read, n_reads, read_len, seed, device):
     return out
 
 
+def nvlink_counters(index):
+    """Sum of this GPU's NVLink data counters (nvidia-smi nvlink -gt d): {"tx_bytes", "rx_bytes"} or None."""
+    import re
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True, timeout=20).stdout
+        tx = [int(x) for x in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out)]
+        rx = [int(x) for x in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out)]
+        if not tx and not rx:
+            return None
+        return {"tx_bytes": sum(tx) * 1024, "rx_bytes": sum(rx) * 1024, "links": len(tx)}
+    except Exception:
+        return None
+
+
 def golden_entry(workload, reads, total_default):
     """Reference-pinned table checksums of the full-size workload (tests/golden/fullsize_golden.json, made by
     tests/golden/make_fullsize_golden.py from the compiled, unmodified reference) -- only for the unmodified read set."""
@@ -619,6 +633,29 @@ def query_arm(args, torch, gb, _capi, L, dev, local_rank, storage, graph, subs, 
     return 0
 
 
+def nvlink_report(nv0, nv1, kmers_rank_total, n_tables, world, ms, peer_bytes=0):
+    """NVLink traffic of rank 0's GPU over the timed region (nvidia-smi counters) beside the algorithmic figure of
+    SURVEY.md section 8d: n_tables x 4 B x (G-1)/G egress per k-mer hashed on this rank."""
+    algo = kmers_rank_total * n_tables * 4 * (world - 1) / world
+    out = {"algorithmic_egress_bytes_rank0": algo, "algorithmic_egress_bytes_per_kmer": n_tables * 4 * (world - 1) / world,
+           "algorithmic_egress_GBps": algo / (ms / 1e3) / 1e9 if ms > 0 else None, "link_peak_GBps_per_direction": 900.0}
+    if nv0 and nv1:
+        tx, rx = nv1["tx_bytes"] - nv0["tx_bytes"], nv1["rx_bytes"] - nv0["rx_bytes"]
+        out.update({"measured_tx_bytes_rank0": tx, "measured_rx_bytes_rank0": rx, "links": nv1.get("links"),
+                    "measured_tx_GBps": tx / (ms / 1e3) / 1e9 if ms > 0 else None,
+                    "measured_tx_bytes_per_kmer": tx / kmers_rank_total if kmers_rank_total else None,
+                    "source": "nvidia-smi nvlink -gt d on rank 0's GPU, before / after the timed region"})
+    else:
+        out["hardware_counters"] = "nvidia-smi nvlink -gt d reports N/A on this box"
+    if peer_bytes:
+        out.update({"peer_store_bytes_rank0": peer_bytes, "peer_store_bytes_per_kmer": peer_bytes / kmers_rank_total if kmers_rank_total else None,
+                    "peer_store_GBps": peer_bytes / (ms / 1e3) / 1e9 if ms > 0 else None,
+                    "peer_store_frac_of_link_peak": peer_bytes / (ms / 1e3) / 1e9 / 900.0 if ms > 0 else None,
+                    "peer_store_source": "software counter: cursors of the buckets rank 0's k_bucket filled in peers' HBM "
+                                         "(entries x 4 B, 16-byte run padding included), summed over the timed region"})
+    return out
+
+
 def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_reads):
     """N > 1: reads sharded over the ranks, every table partitioned by slot range, one bucket
     exchange (NCCL all-to-all) per round.  Strong scaling: the workload's read set is fixed."""
@@ -674,6 +711,10 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
     dist.barrier()
     torch.cuda.synchronize()
     _capi.check(L.gt_profile_enable(1), "gt_profile_enable")
+    st.peer_store_bytes(reset=True)
+    nv0 = nvlink_counters(local_rank) if rank == 0 else None  # before the barrier: not inside the timed region
+    dist.barrier()
+    torch.cuda.synchronize()
     sampler.begin()
     launches0 = L.gt_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -685,6 +726,9 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
     st.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
+    nv1 = nvlink_counters(local_rank) if rank == 0 else None
+    peer_bytes = st.peer_store_bytes()
+    dist.barrier()
     t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
@@ -817,6 +861,7 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
                          "kernels": {name: {"launches": int(prof_n[i]), "ms_total": float(prof_ms[i]),
                                             "share_of_step": float(prof_ms[i] / ms) if ms > 0 else 0.0}
                                      for i, name in enumerate(("k_bucket", "k_apply")) if prof_n[i]}},
+            "nvlink": nvlink_report(nv0, nv1, kmers_rank * args.steps, n_tables, world, ms, peer_bytes),
             "cpu_baseline": None,
             "check": check,
         }

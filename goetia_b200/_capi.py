@@ -93,6 +93,10 @@ SIGNATURES = {
     "gt_storage_inbox_bytes": (C.c_uint64, [C.c_void_p, C.c_int]),
     "gt_storage_attach_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gt_query_hashes_local_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "gt_shard_route_hashes_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "gt_shard_answer_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "gt_shard_insert_requests_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "gt_hash_values_dev": (C.c_int64, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "gt_storage_select_store": (C.c_int, [C.c_void_p, C.c_int]),
     "gt_storage_apply_store": (C.c_int, [C.c_void_p, C.c_int]),
     "gt_set_compute_stream": (C.c_int, [C.c_void_p]),

@@ -1551,6 +1551,130 @@ extern "C" int gt_query_hashes_local_dev(gt_storage* st, const void* d_hashes, u
     return 0;
 }
 
+static int scan_counts(Slot& sl, const uint64_t* d_in, uint64_t n, uint64_t* d_out, cudaStream_t s);
+// ---- owner-routed requests (kernels.cuh, k_route_requests ...) -------------------------------------------------------
+static int shard_ready(const char* who, gt_storage* st) {
+    if (ensure_ctx()) return -1;
+    if (!st || !st->pend || st->world < 2) return fail("%s: not a sharded storage", who);
+    if (st->pend->pending_total()) return fail("%s: updates are pending (exchange and apply first)", who);
+    CU(cudaSetDevice(g_ctx.device));
+    if (g_ctx.apply) {  // must see every applied update
+        cudaEvent_t& ev = g_ctx.slot[0].packed;
+        CU(cudaEventRecord(ev, g_ctx.apply));
+        CU(cudaStreamWaitEvent(g_ctx.main, ev, 0));
+    }
+    return 0;
+}
+// d_req[n * n_tables] (uint64: table << 59 | slot) and d_owner[n * n_tables] (int32 rank) for n hash values
+extern "C" int gt_shard_route_hashes_dev(gt_storage* st, const void* d_hashes, uint64_t n, void* d_req, void* d_owner) {
+    if (ensure_ctx()) return -1;
+    if (!st || !st->pend || st->world < 2) return fail("gt_shard_route_hashes_dev: not a sharded storage");
+    if (n == 0) return 0;
+    if (!d_hashes || !d_req || !d_owner) return fail("gt_shard_route_hashes_dev: NULL argument");
+    CU(cudaSetDevice(g_ctx.device));
+    RouteArgs ra;
+    memset(&ra, 0, sizeof ra);
+    const PlanHost& H = st->pend->host;
+    for (int t = 0; t < st->n; ++t) ra.spr[t] = std::max<uint64_t>(1, H.own_hi[t] - H.own_lo[t]);  // rank 0's share = every rank's
+    k_route_requests<<<grid_for(n, 256, 8), 256, 0, g_ctx.main>>>(static_cast<const uint64_t*>(d_hashes), n, st->ts, ra,
+                                                                   static_cast<unsigned long long*>(d_req), static_cast<int32_t*>(d_owner));
+    ++g_launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+// owner side of a routed query: d_answers[i] (uint8) = the slot of request i (bit, or counter value)
+extern "C" int gt_shard_answer_dev(gt_storage* st, const void* d_req, uint64_t n_req, void* d_answers) {
+    if (shard_ready("gt_shard_answer_dev", st)) return -1;
+    if (n_req == 0) return 0;
+    if (!d_req || !d_answers) return fail("gt_shard_answer_dev: NULL argument");
+    const unsigned long long* r = static_cast<const unsigned long long*>(d_req);
+    uint8_t* a = static_cast<uint8_t*>(d_answers);
+    const int g = grid_for(n_req, 256, 8);
+    if (st->kind == 0) k_answer_requests<0><<<g, 256, 0, g_ctx.main>>>(r, n_req, st->ts, a);
+    else if (st->kind == 1) k_answer_requests<1><<<g, 256, 0, g_ctx.main>>>(r, n_req, st->ts, a);
+    else k_answer_requests<2><<<g, 256, 0, g_ctx.main>>>(r, n_req, st->ts, a);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+// owner side of a routed insert: apply the requests; with d_ord (uint32 serial ordinals assigned by the sources) also
+// d_first[i] = 1 iff request i is the FIRST toucher (smallest ordinal of this call) of a slot that was zero before the call
+extern "C" int gt_shard_insert_requests_dev(gt_storage* st, const void* d_req, const void* d_ord, uint64_t n_req, void* d_first) {
+    if (shard_ready("gt_shard_insert_requests_dev", st)) return -1;
+    if (n_req == 0) return 0;
+    if (!d_req) return fail("gt_shard_insert_requests_dev: NULL argument");
+    if (d_first && !d_ord) return fail("gt_shard_insert_requests_dev: first-toucher flags need ordinals");
+    const unsigned long long* r = static_cast<const unsigned long long*>(d_req);
+    const uint32_t* o = static_cast<const uint32_t*>(d_ord);
+    uint8_t* f = static_cast<uint8_t*>(d_first);
+    cudaStream_t s = g_ctx.main;
+    ClaimMap cm;
+    memset(&cm, 0, sizeof cm);
+    const int g = grid_for(n_req, 256, 8);
+    if (o) {
+        if (exact_map(n_req, s, cm)) return -1;
+        if (st->kind == 0) k_claim_requests<0><<<g, 256, 0, s>>>(r, o, n_req, st->ts, cm);
+        else if (st->kind == 1) k_claim_requests<1><<<g, 256, 0, s>>>(r, o, n_req, st->ts, cm);
+        else k_claim_requests<2><<<g, 256, 0, s>>>(r, o, n_req, st->ts, cm);
+        ++g_launches;
+    }
+    if (st->kind == 0) k_insert_requests<0><<<g, 256, 0, s>>>(r, o, n_req, st->ts, cm, f);
+    else if (st->kind == 1) k_insert_requests<1><<<g, 256, 0, s>>>(r, o, n_req, st->ts, cm, f);
+    else k_insert_requests<2><<<g, 256, 0, s>>>(r, o, n_req, st->ts, cm, f);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// KmerIterator over reads resident in HBM: d_values (uint64, capacity >= n_bases) receives hash_type::value() of every
+// k-mer (the canonical minimum for GT_SHIFTER_CAN), reads back to back; returns the number of k-mers (one 8-byte read-back).
+extern "C" int64_t gt_hash_values_dev(int shifter, int K, const void* d_bases, const void* d_offsets, uint64_t n_reads, uint64_t n_bases,
+                                       void* d_values) {
+    if (ensure_ctx()) return -1;
+    if (K < 1 || K > 65535) return fail("gt_hash_values_dev: K=%d out of range (1..65535)", K);
+    if (n_reads == 0) return 0;
+    if (!d_bases || !d_offsets || !d_values) return fail("gt_hash_values_dev: NULL device pointer");
+    if ((reinterpret_cast<uintptr_t>(d_bases) & 15) || (reinterpret_cast<uintptr_t>(d_offsets) & 7))
+        return fail("gt_hash_values_dev: d_bases must be 16-byte aligned and d_offsets 8-byte aligned");
+    if (n_reads >= (1ull << 32)) return fail("gt_hash_values_dev: too many reads");
+    CU(cudaSetDevice(g_ctx.device));
+    Slot& sl = g_ctx.slot[0];
+    cudaStream_t s = g_ctx.main;
+    if (sl.consumed_pending) {
+        CU(cudaStreamWaitEvent(s, sl.consumed, 0));
+        sl.consumed_pending = false;
+    }
+    CU(cudaStreamSynchronize(sl.stream));
+    const uint64_t n_words = (n_bases + 31) / 32, n_words_alloc = n_words + halo_alloc_words();
+    if (sl.words.reserve(n_words_alloc * 8, s) || sl.flags.reserve(n_reads + 1, s) || sl.coarse.reserve(((n_bases >> COARSE_SHIFT) + 2) * 4, s) ||
+        sl.kcount.reserve(n_reads * 8, s) || sl.koff.reserve(n_reads * 8, s))
+        return -1;
+    const uint64_t* offs = static_cast<const uint64_t*>(d_offsets);
+    if (pack_on_device(static_cast<const uint8_t*>(d_bases), offs, n_reads, n_bases, 0, sl.words.as<uint64_t>(), n_words_alloc,
+                       sl.flags.as<uint8_t>(), sl.coarse.as<uint32_t>(), s))
+        return -1;
+    gt_batch view;
+    view.n_reads = n_reads;
+    view.n_bases = n_bases;
+    view.n_words = n_words;
+    view.n_words_alloc = n_words_alloc;
+    view.base0 = 0;
+    view.d_words = sl.words.as<uint64_t>();
+    view.d_offsets = const_cast<uint64_t*>(offs);
+    view.d_flags = sl.flags.as<uint8_t>();
+    view.d_coarse = sl.coarse.as<uint32_t>();
+    const int64_t nk = batch_kmers(view, K, sl.kcount.as<uint64_t>(), nullptr, s);
+    if (nk < 0) return -1;
+    if (scan_counts(sl, sl.kcount.as<uint64_t>(), n_reads, sl.koff.as<uint64_t>(), s)) return -1;
+    WalkArgs a = make_args(view, K);
+    a.koff = sl.koff.as<uint64_t>();
+    a.fw = static_cast<uint64_t*>(d_values);
+    a.rc = nullptr;  // value() only
+    if (launch_hash(shifter, a, s)) return -1;
+    CU(cudaStreamSynchronize(s));
+    return nk;
+}
+
 // A sharded storage can hold two buffer sets so that the exchange of one round overlaps the
 // hashing of the next: choose the set the next inserts bucket into.
 extern "C" int gt_storage_select_store(gt_storage* st, int which) {

@@ -654,8 +654,11 @@ k_walk(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts) 
                         a.counts[a.koff[r] + (p - rstart)] = (int16_t)storage_query<KIND, NT>(ts, h);
                     } else if constexpr (OP == OP_HASH) {
                         uint64_t o = a.koff[r] + (p - rstart);
-                        a.fw[o] = fw;
-                        if (CAN) a.rc[o] = rc;
+                        if (CAN && !a.rc) a.fw[o] = h;  // value() only (routed queries on a sharded storage)
+                        else {
+                            a.fw[o] = fw;
+                            if (CAN) a.rc[o] = rc;
+                        }
                     } else {
                         acc += storage_query<KIND, NT>(ts, h) >= a.cutoff;
                     }
@@ -823,6 +826,56 @@ __global__ void __launch_bounds__(256) k_query_hashes_local(const uint64_t* __re
             }
         }
         counts[i] = (int16_t)acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Owner-routed requests on a sharded storage ("queries: same forward route; owners answer with the
+// bit / count, 1 B per message"; tracked inserts: first-toucher flags travel back the same way).
+// A request = (table << 59 | global slot).  Rank q holds slots [q * spr[t], (q + 1) * spr[t]) of table t.
+// ------------------------------------------------------------------------------------------
+struct RouteArgs { uint64_t spr[MAX_TABLES]; };
+__global__ void __launch_bounds__(256) k_route_requests(const uint64_t* __restrict__ hashes, uint64_t n, const __grid_constant__ TableSet ts,
+                                                         const __grid_constant__ RouteArgs ra, unsigned long long* __restrict__ req,
+                                                         int32_t* __restrict__ owner) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t h = hashes[i];
+        for (int t = 0; t < ts.n; ++t) {
+            const uint64_t bin = fastmod_u64(h, ts.size[t], ts.magic[t]);
+            req[i * ts.n + t] = ((unsigned long long)t << 59) | bin;
+            owner[i * ts.n + t] = (int32_t)(bin / ra.spr[t]);
+        }
+    }
+}
+template <int KIND>
+__global__ void __launch_bounds__(256) k_answer_requests(const unsigned long long* __restrict__ req, uint64_t n, const __grid_constant__ TableSet ts,
+                                                          uint8_t* __restrict__ ans) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long r = req[i];
+        ans[i] = (uint8_t)slot_query<KIND>(ts.ptr[(int)(r >> 59)], r & ((1ull << 59) - 1));
+    }
+}
+// tracked insert of routed requests, serial first-toucher rule over the ordinals the sources assigned (GT_MODE_EXACT's
+// two passes, kernels.cuh "GT_MODE_EXACT", on messages instead of k-mers)
+template <int KIND>
+__global__ void __launch_bounds__(256) k_claim_requests(const unsigned long long* __restrict__ req, const uint32_t* __restrict__ ord, uint64_t n,
+                                                         const __grid_constant__ TableSet ts, const ClaimMap m) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long r = req[i];
+        const int t = (int)(r >> 59);
+        const uint64_t bin = r & ((1ull << 59) - 1);
+        if (slot_query<KIND>(ts.ptr[t], bin) == 0) claim_post(m, claim_key(t, bin), ord[i]);
+    }
+}
+template <int KIND>
+__global__ void __launch_bounds__(256) k_insert_requests(const unsigned long long* __restrict__ req, const uint32_t* __restrict__ ord, uint64_t n,
+                                                          const __grid_constant__ TableSet ts, const ClaimMap m, uint8_t* __restrict__ first) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long r = req[i];
+        const int t = (int)(r >> 59);
+        const uint64_t bin = r & ((1ull << 59) - 1);
+        if (first) first[i] = ord && claim_winner(m, claim_key(t, bin)) == ord[i] ? 1 : 0;
+        slot_insert<KIND, false>(ts.ptr[t], bin);
     }
 }
 

@@ -141,6 +141,44 @@ class ShardExchange:
         return self.inbox[o:o + n]
 
 
+class ShardRouter:
+    """Owner-routed requests: the collective plumbing, on any torch device / backend.
+
+    A source rank turns its hash values into requests (table << 59 | slot) with an owner rank each; `route` ships every
+    request to its owner with one all-to-all of counts and one of payloads, `ship` sends a second payload (e.g. serial
+    ordinals) along the same route, and `back` returns one answer per request along the reverse route and puts the answers
+    in request order.  The compute (making requests, answering them) is done by the caller -- CUDA kernels through the C
+    ABI on a GPU, numpy in the gloo tests."""
+
+    def __init__(self, torch, dist, world, group=None):
+        self.torch, self.dist, self.world, self.group = torch, dist, world, group
+
+    def route(self, req, owner):
+        torch, dist = self.torch, self.dist
+        order = torch.argsort(owner, stable=True)
+        send = torch.bincount(owner, minlength=self.world).to(torch.int64)
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)
+        send_l, recv_l = [int(x) for x in send.tolist()], [int(x) for x in recv.tolist()]
+        got = torch.empty(sum(recv_l), dtype=req.dtype, device=req.device)
+        dist.all_to_all_single(got, req[order].contiguous(), recv_l, send_l, group=self.group)
+        return (order, send_l, recv_l), got
+
+    def ship(self, handle, payload):
+        order, send_l, recv_l = handle
+        got = self.torch.empty(sum(recv_l), dtype=payload.dtype, device=payload.device)
+        self.dist.all_to_all_single(got, payload[order].contiguous(), recv_l, send_l, group=self.group)
+        return got
+
+    def back(self, handle, answers):
+        order, send_l, recv_l = handle
+        got = self.torch.empty(sum(send_l), dtype=answers.dtype, device=answers.device)
+        self.dist.all_to_all_single(got, answers.contiguous(), send_l, recv_l, group=self.group)
+        out = self.torch.empty_like(got)
+        out[order] = got
+        return out
+
+
 class ShardedStorage:
     """This rank's part of a BitStorage / ByteStorage / NibbleStorage sharded over the process group.
 
@@ -284,6 +322,13 @@ class ShardedStorage:
                 if self._applied[w ^ 1] is not None:
                     self.stream.wait_event(self._applied[w ^ 1])
                 torch.index_select(self.fill_send[w], 0, self._perm, out=self._fx[w])
+                # software NVLink counter: entries this rank stored into peers' inboxes this round (cursors of foreign
+                # buckets, 16-byte run padding included); nvidia-smi's link counters are not available on every box
+                if getattr(self, "_foreign", None) is None:
+                    own = torch.as_tensor(np.asarray(plan.owner) != self.rank, device=self.device)
+                    self._foreign = own.to(torch.int64)
+                    self._peer_entries = torch.zeros(1, dtype=torch.int64, device=self.device)
+                self._peer_entries += (self.fill_send[w][:plan.nb].to(torch.int64) * self._foreign).sum()
                 dist.all_to_all_single(self.fill_recv[w], self._fx[w], self._fill_out, self._fill_in, group=self.group)
             ev = torch.cuda.Event()
             ev.record(self.stream)
@@ -293,6 +338,17 @@ class ShardedStorage:
         done.record(self.apply_stream)
         self._applied[w] = done
         self.cur = w ^ 1
+
+    def peer_store_bytes(self, reset=False):
+        """Bytes this rank's k_bucket stored straight into peers' HBM over NVLink since the last reset (p2p transport;
+        counted from the bucket cursors, so the 16-byte run padding is included).  Synchronises."""
+        if getattr(self, "_peer_entries", None) is None:
+            return 0
+        self.synchronize()
+        v = int(self._peer_entries.item()) * 4
+        if reset:
+            self._peer_entries.zero_()
+        return v
 
     def join(self):
         """Order the compute stream after every k_apply queued so far (no host wait): an event
@@ -305,52 +361,202 @@ class ShardedStorage:
         self.stream.synchronize()
         self.apply_stream.synchronize()
 
-    # ---- routed queries: every rank answers for the slots it holds ----------
-    def query_hashes(self, hashes):
-        """Storage::query for a vector of hash values (collective; every rank may pass its own,
-        differently sized vector and gets its own answers back): the values are all-gathered, each
-        rank answers for the slots it holds (gt_query_hashes_local_dev) and an all-reduce MIN
-        combines the answers -- AND of bits / min of counters over all tables."""
-        torch, dist = self.torch, self.dist
-        h = np.ascontiguousarray(hashes, dtype=np.uint64)
-        W, dev = self.world, self.device
-        self.synchronize()
+    # ---- owner-routed queries and tracked inserts ---------------------------------------------
+    def _router(self):
+        if getattr(self, "_rt", None) is None:
+            self._rt = ShardRouter(self.torch, self.dist, self.world, self.group)
+        return self._rt
+
+    def _requests(self, values):
+        """values: int64 device tensor of hash values -> (requests int64 [m * T], owners int64 [m * T])"""
+        torch = self.torch
+        T, m = int(self._sizes.size), int(values.numel())
+        req = torch.empty(max(m * T, 1), dtype=torch.int64, device=self.device)
+        owner = torch.empty(max(m * T, 1), dtype=torch.int32, device=self.device)
+        _capi.check(_capi.lib().gt_shard_route_hashes_dev(self._h, values.data_ptr(), m, req.data_ptr(), owner.data_ptr()),
+                    "gt_shard_route_hashes_dev")
+        return req[:m * T], owner[:m * T].to(torch.int64)
+
+    def query_hashes_dev(self, values):
+        """Storage::query for a device tensor of hash values (collective; every rank passes its own, differently sized
+        vector): each (hash, table) request travels to the rank that holds the slot (8 B), the owner answers with the
+        slot's value (1 B), and the source takes the AND / min over the tables (bitstorage.cc:87-100, bytestorage.cc:
+        116-139, nibblestorage.cc:112-130).  -> int16 device tensor."""
+        torch = self.torch
+        T, m = int(self._sizes.size), int(values.numel())
+        self.join()
         with torch.cuda.stream(self.stream):
-            n = torch.tensor([h.size], dtype=torch.int64, device=dev)
-            ns = torch.empty(W, dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(ns, n, group=self.group)
-            m = int(ns.max().item())
-            if m == 0:
-                return np.zeros(0, dtype=np.int16)
-            mine = torch.zeros(m, dtype=torch.int64, device=dev)
-            if h.size:
-                mine[:h.size] = torch.from_numpy(h.view(np.int64)).to(dev)
-            allh = torch.empty(W * m, dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(allh, mine, group=self.group)
-            counts = torch.empty(W * m, dtype=torch.int16, device=dev)
-            self.stream.synchronize()
-            _capi.check(_capi.lib().gt_query_hashes_local_dev(self._h, allh.data_ptr(), W * m, counts.data_ptr()),
-                        "gt_query_hashes_local_dev")
-            c32 = counts.to(torch.int32)  # NCCL has no 16-bit integer type
-            dist.all_reduce(c32, op=dist.ReduceOp.MIN, group=self.group)
-            out = c32[self.rank * m:self.rank * m + h.size].to(torch.int16).cpu().numpy()
+            req, owner = self._requests(values)
+            handle, got = self._router().route(req, owner)
+            ans = torch.empty(max(got.numel(), 1), dtype=torch.uint8, device=self.device)
+            _capi.check(_capi.lib().gt_shard_answer_dev(self._h, got.data_ptr(), got.numel(), ans.data_ptr()), "gt_shard_answer_dev")
+            back = self._router().back(handle, ans[:got.numel()])
+            out = back.view(m, T).amin(dim=1).to(torch.int16) if m else torch.zeros(0, dtype=torch.int16, device=self.device)
+        self.stream.synchronize()
         return out
 
-    def query_sequences(self, shifter_kind, K, bases, offsets):
-        """dBG::query_sequence over a host batch against the sharded tables (collective)."""
+    def query_hashes(self, hashes):
+        h = np.ascontiguousarray(hashes, dtype=np.uint64)
+        v = self.torch.from_numpy(h.view(np.int64)).to(self.device)
+        return self.query_hashes_dev(v).cpu().numpy()
+
+    def _hash_values_dev(self, shifter_kind, K, bases, offsets):
+        """host reads -> int64 device tensor of hash values (value() of every k-mer, reads back to back)"""
+        torch = self.torch
         bases, offsets = _capi.as_reads(bases, offsets)
-        n_reads = offsets.size - 1
-        lens = (offsets[1:] - offsets[:-1]).astype(np.int64)
-        cap = int(np.maximum(lens - K + 1, 0).sum())
-        fw = np.empty(max(cap, 1), dtype=np.uint64)
-        rc = np.empty(max(cap, 1), dtype=np.uint64)
+        n_reads, n_bases = offsets.size - 1, int(offsets[-1] - offsets[0]) if offsets.size > 1 else 0
+        vals = torch.empty(max(n_bases, 1), dtype=torch.int64, device=self.device)
         nk = 0
-        if n_reads:
-            nk = int(_capi.check(_capi.lib().gt_hash_sequences(shifter_kind, K, bases.ctypes.data, offsets.ctypes.data,
-                                                               n_reads, fw.ctypes.data, rc.ctypes.data, None),
-                                 "gt_hash_sequences"))
-        v = np.minimum(fw[:nk], rc[:nk]) if shifter_kind == _capi.SHIFTER_CAN else fw[:nk]
-        return self.query_hashes(v)
+        if n_reads and n_bases:
+            with torch.cuda.stream(self.stream):
+                pad = np.zeros(n_bases + 16, dtype=np.uint8)
+                pad[:n_bases] = bases[int(offsets[0]):int(offsets[-1])]
+                d_b = torch.from_numpy(pad).to(self.device)
+                d_o = torch.from_numpy((offsets - offsets[0]).view(np.int64)).to(self.device)
+                self.stream.synchronize()
+                nk = int(_capi.check(_capi.lib().gt_hash_values_dev(shifter_kind, K, d_b.data_ptr(), d_o.data_ptr(), n_reads, n_bases,
+                                                                    vals.data_ptr()), "gt_hash_values_dev"))
+        return vals[:nk]
+
+    def query_sequences(self, shifter_kind, K, bases, offsets):
+        """dBG::query_sequence over a host batch against the sharded tables (collective): hashed on the device, then
+        owner-routed."""
+        return self.query_hashes_dev(self._hash_values_dev(shifter_kind, K, bases, offsets)).cpu().numpy()
+
+    def insert_hashes_tracked_dev(self, values):
+        """Storage::insert for a device tensor of hash values with the reference's return value (collective): is_new[i]
+        = the hash found a slot that was empty and no earlier hash of this call (ranks in order, each rank's hashes
+        in order) had touched it -- the serial first-toucher rule.  Requests travel to the owners
+        with their serial ordinals, the owners answer with one flag per request (the n_unique reverse route of
+        section 8e), the source ORs a hash's flags.  -> uint8 device tensor; n_unique_kmers() is updated."""
+        torch, dist = self.torch, self.dist
+        T, m = int(self._sizes.size), int(values.numel())
+        self.join()
+        with torch.cuda.stream(self.stream):
+            ns = torch.empty(self.world, dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(ns, torch.tensor([m], dtype=torch.int64, device=self.device), group=self.group)
+            ns_l = [int(x) for x in ns.tolist()]
+            if sum(ns_l) >= 2**32:
+                raise _capi.GoetiaB200Error("insert_hashes_tracked: more than 2^32-1 hashes in one call")
+            base = sum(ns_l[:self.rank])
+            req, owner = self._requests(values)
+            ords = (base + torch.arange(m, dtype=torch.int64, device=self.device)).repeat_interleave(T).to(torch.int32)
+            handle, got = self._router().route(req, owner)
+            got_ord = self._router().ship(handle, ords)
+            first = torch.zeros(max(got.numel(), 1), dtype=torch.uint8, device=self.device)
+            _capi.check(_capi.lib().gt_shard_insert_requests_dev(self._h, got.data_ptr(), got_ord.data_ptr(), got.numel(),
+                                                                 first.data_ptr()), "gt_shard_insert_requests_dev")
+            back = self._router().back(handle, first[:got.numel()])
+            is_new = back.view(m, T).amax(dim=1) if m else torch.zeros(0, dtype=torch.uint8, device=self.device)
+            tot = is_new.sum(dtype=torch.int64).reshape(1)
+            dist.all_reduce(tot, group=self.group)
+            self._n_unique = getattr(self, "_n_unique", 0) + int(tot.item())
+        self.stream.synchronize()
+        return is_new
+
+    def insert_sequences_tracked(self, shifter_kind, K, bases, offsets):
+        """dBG::insert_sequence(sequence, n_new) over a host batch on the sharded tables (collective): -> (k-mers
+        consumed, n_new per read) under the serial rule, ranks in order."""
+        torch = self.torch
+        bases, offsets = _capi.as_reads(bases, offsets)
+        vals = self._hash_values_dev(shifter_kind, K, bases, offsets)
+        is_new = self.insert_hashes_tracked_dev(vals)
+        n = offsets.size - 1
+        lens = (offsets[1:] - offsets[:-1]).astype(np.int64)
+        ok = np.ones(n, dtype=bool)
+        if n:
+            valid = np.zeros(256, dtype=bool)
+            valid[np.frombuffer(b"ACGTacgt", dtype=np.uint8)] = True
+            bad = np.concatenate([[0], np.cumsum(~valid[bases[int(offsets[0]):int(offsets[-1])]])])
+            rel = (offsets - offsets[0]).astype(np.int64)
+            ok = (bad[rel[1:]] - bad[rel[:-1]]) == 0
+        nk = np.where(ok, np.maximum(lens - K + 1, 0), 0)
+        flags = is_new.cpu().numpy().astype(np.int64)
+        ends = np.cumsum(nk)
+        csum = np.concatenate([[0], np.cumsum(flags)])
+        n_new = csum[ends] - csum[ends - nk]
+        return int(nk.sum()), n_new.astype(np.uint64)
+
+    def n_unique_kmers(self):
+        """Running sum of the tracked inserts' is_new over all ranks (blind inserts do not maintain it)."""
+        return int(getattr(self, "_n_unique", 0))
+
+    # ---- OXLI v4 files of the WHOLE storage (bitstorage.cc:151-307, bytestorage.cc:480-536, nibblestorage.cc:132-278) ---
+    def _file_layout(self):
+        kind = self.kind
+        head = 6 + (1 if kind == _capi.STORAGE_BYTE else 0) + 13
+        starts, pos = [], head
+        for size in self._sizes.tolist():
+            size = int(size)
+            starts.append(pos + 8)
+            pos += 8 + (size // 8 + 1 if kind == 0 else size if kind == 1 else size // 2 + 1)
+        return head, starts, pos
+
+    def save(self, filename, ksize):
+        """Collective: one OXLI file holding the whole storage, byte-identical to what a single-GPU storage (and the
+        reference) writes for the same contents: rank 0 writes the header, every rank writes its slot ranges in place."""
+        import struct
+        kind, n_occ = self.kind, self.n_occupied()
+        head, starts, total = self._file_layout()
+        parts = self.local_tables()
+        if self.rank == 0:
+            with open(filename, "wb") as f:
+                f.write(b"OXLI")
+                f.write(struct.pack("<BB", 4, {0: 2, 1: 1, 2: 7}[kind]))
+                if kind == _capi.STORAGE_BYTE:
+                    f.write(struct.pack("<B", 0))
+                f.write(struct.pack("<IBQ", int(ksize), int(self._sizes.size), n_occ))
+                f.truncate(total + (8 if kind == _capi.STORAGE_BYTE else 0))
+        self.dist.barrier(group=self.group)
+        spb = {0: 8, 1: 1, 2: 2}[kind]
+        with open(filename, "r+b") as f:
+            for i, size in enumerate(self._sizes.tolist()):
+                lo, _ = self.local_range(i)
+                if self.rank == 0:
+                    f.seek(starts[i] - 8)
+                    f.write(struct.pack("<Q", int(size)))
+                if parts[i].size:
+                    f.seek(starts[i] + lo // spb)
+                    f.write(parts[i].tobytes())
+            if self.rank == 0 and kind == _capi.STORAGE_BYTE:
+                f.seek(total)
+                f.write(struct.pack("<Q", 0))  # n_bigcounts
+        self.dist.barrier(group=self.group)
+
+    def load(self, filename):
+        """Collective: every rank reads its slot ranges of an OXLI file (written by any goetia storage of the same kind and
+        table sizes) into its part.  Returns the saved ksize."""
+        import struct
+        kind = self.kind
+        head, starts, total = self._file_layout()
+        spb = {0: 8, 1: 1, 2: 2}[kind]
+        L = _capi.lib()
+        self.synchronize()
+        with open(filename, "rb") as f:
+            hdr = f.read(head)
+            if len(hdr) < head or hdr[:4] != b"OXLI":
+                raise _capi.GoetiaB200Error("Does not start with signature for a oxli binary file")
+            if hdr[4] != 4 or hdr[5] != {0: 2, 1: 1, 2: 7}[kind]:
+                raise _capi.GoetiaB200Error("Incorrect file format version / type")
+            ksize, n_tables, _occ = struct.unpack_from("<IBQ", hdr, head - 13)
+            if n_tables != self._sizes.size:
+                raise _capi.GoetiaB200Error("table count differs from this storage's")
+            for i, size in enumerate(self._sizes.tolist()):
+                f.seek(starts[i] - 8)
+                (fsize,) = struct.unpack("<Q", f.read(8))
+                if fsize != int(size):
+                    raise _capi.GoetiaB200Error("table sizes differ from this storage's")
+                lo, _ = self.local_range(i)
+                nb = int(L.gt_storage_table_bytes(self._h, i))
+                f.seek(starts[i] + lo // spb)
+                buf = np.frombuffer(f.read(nb), dtype=np.uint8)
+                if buf.size != nb:
+                    raise _capi.GoetiaB200Error("truncated table")
+                buf = np.ascontiguousarray(buf)
+                _capi.check(L.gt_storage_upload_table(self._h, i, buf.ctypes.data), "gt_storage_upload_table")
+        self._n_unique = 0
+        self.dist.barrier(group=self.group)
+        return int(ksize)
 
     def local_range(self, i):
         lo, hi = np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint64)
@@ -402,6 +608,7 @@ class ShardedStorage:
     def reset(self):
         self.synchronize()
         _capi.check(_capi.lib().gt_storage_reset(self._h), "gt_storage_reset")
+        self._n_unique = 0
 
     def close(self, collective=True):
         """Collective when the transport is p2p (barriers keep a peer from storing into, or

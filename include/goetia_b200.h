@@ -340,6 +340,23 @@ int gt_storage_attach_peers(gt_storage* st, int which, void* const* inbox_of_ran
  * nibblestorage.cc:112-130).  d_hashes / d_counts are device pointers; asynchronous on the
  * compute stream. */
 int gt_query_hashes_local_dev(gt_storage* st, const void* d_hashes, uint64_t n, void* d_counts);
+/* Owner-routed requests ("owners answer with the bit / count, 1 B per message"; the n_unique
+ * reverse route of tracked inserts).  A request is (table << 59 | global slot), 8 bytes.
+ *   gt_shard_route_hashes_dev  for n hash values: d_req[n * n_tables] requests and d_owner[n * n_tables] (int32) = the rank
+ *                              holding each slot; the caller ships the requests to their owners (all-to-all);
+ *   gt_shard_answer_dev        owner side of a query: d_answers[i] (uint8) = value of the slot of request i; the source
+ *                              takes the AND / min over a hash's n_tables answers = Storage::query;
+ *   gt_shard_insert_requests_dev  owner side of an insert: applies the requests; with d_ord (uint32 serial ordinals given by
+ *                              the sources) d_first[i] = 1 iff request i is the first toucher of a slot that was empty
+ *                              (GT_MODE_EXACT's rule); the source ORs a hash's flags = Storage::insert's return value.
+ * All device pointers; asynchronous on the compute stream. */
+int gt_shard_route_hashes_dev(gt_storage* st, const void* d_hashes, uint64_t n, void* d_req, void* d_owner);
+int gt_shard_answer_dev(gt_storage* st, const void* d_req, uint64_t n_req, void* d_answers);
+int gt_shard_insert_requests_dev(gt_storage* st, const void* d_req, const void* d_ord, uint64_t n_req, void* d_first);
+/* KmerIterator over reads resident in HBM (ASCII d_bases, uint64 d_offsets from 0): d_values (uint64, capacity >= n_bases)
+ * receives hash_type::value() of every k-mer, reads back to back.  Returns the number of k-mers. */
+int64_t gt_hash_values_dev(int shifter, int K, const void* d_bases, const void* d_offsets, uint64_t n_reads,
+                           uint64_t n_bases, void* d_values);
 /* Run the library's kernels on caller-owned CUDA streams (NULL = the library's own), so that
  * they order with the caller's collectives: the compute stream carries pack / hash / bucket,
  * the apply stream k_apply. */

@@ -51,6 +51,98 @@ def np_apply(kind, slab, local_slots):
             slab[:] = (slab & (0xF0 if sh == 0 else 0x0F)) | (new << sh)
 
 
+def route_mode(kind, rank, world, K, sizes, bases, offsets, my_b, my_o, budget, slice_log2):
+    """gloo: ShardRouter's plumbing (route / ship / back) with the owner-side compute emulated in numpy on the oracle's
+    tables: routed queries and the first-toucher flags of a tracked insert must equal the oracle's serial answers."""
+    from goetia_b200.shard import ShardRouter
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    plan = ShardPlan(kind, sizes, world, budget, slice_log2)
+    T = len(sizes)
+    spr = [max(1, int(plan.own_hi[0, t] - plan.own_lo[0, t])) for t in range(T)]
+    rt = ShardRouter(torch, dist, world)
+
+    def requests(values):
+        req = np.zeros(values.size * T, dtype=np.uint64)
+        own = np.zeros(values.size * T, dtype=np.int64)
+        for t in range(T):
+            b = values % np.uint64(sizes[t])
+            req[t::T] = (np.uint64(t) << np.uint64(59)) | b
+            own[t::T] = (b // np.uint64(spr[t])).astype(np.int64)
+        return torch.from_numpy(req.view(np.int64)), torch.from_numpy(own)
+
+    def hashes_of(b, o):
+        out = []
+        for r in range(o.size - 1):
+            fw, rc = Port.hash_sequence(1, K, b[int(o[r]):int(o[r + 1])].tobytes().decode())
+            out.append(np.minimum(fw, rc))
+        return np.concatenate(out) if out else np.zeros(0, dtype=np.uint64)
+
+    # the state the owners answer from: the oracle's tables after the first half of the reads (every rank holds a copy and
+    # answers only for the slots it owns -- a request for a foreign slot is an error of the routing)
+    half = (offsets.size - 1) // 2
+    ref = Port(kind, 1, K, sizes)
+    ref.insert_reads(bases[:int(offsets[half])], offsets[:half + 1])
+
+    def slot_values(got):
+        g = got.numpy().view(np.uint64)
+        t = (g >> np.uint64(59)).astype(np.int64)
+        b = g & np.uint64((1 << 59) - 1)
+        out = np.zeros(g.size, dtype=np.uint8)
+        for i in range(g.size):
+            assert plan.own_lo[rank, t[i]] <= b[i] < plan.own_hi[rank, t[i]], "request routed to the wrong owner"
+            tab = tabs[int(t[i])]
+            bb = int(b[i])
+            out[i] = ((tab[bb >> 3] >> (bb & 7)) & 1) if kind == 0 else tab[bb] if kind == 1 else (
+                (tab[bb >> 1] & 15) if (bb & 1) else (tab[bb >> 1] >> 4))
+        return out
+
+    tabs = ref.tables()
+    vals = hashes_of(my_b, my_o)
+    req, own = requests(vals)
+    handle, got = rt.route(req, own)
+    ans = torch.from_numpy(slot_values(got))
+    back = rt.back(handle, ans).numpy().reshape(-1, T)
+    got_q = back.min(axis=1).astype(np.int16) if vals.size else np.zeros(0, dtype=np.int16)
+    want_q = ref.query_hashes(vals)
+    ok = np.array_equal(got_q, want_q)
+    # tracked insert of ALL reads' hashes on top: first-toucher flags by serial ordinal (ranks in order)
+    ns = [None] * world
+    dist.all_gather_object(ns, int(vals.size))
+    base = sum(ns[:rank])
+    ords = torch.from_numpy(np.repeat(base + np.arange(vals.size, dtype=np.int64), T))
+    got_ord = rt.ship(handle, ords).numpy()
+    g = got.numpy().view(np.uint64)
+    zero_before = slot_values(got) == 0
+    first = np.zeros(g.size, dtype=np.uint8)
+    winners = {}
+    for i in range(g.size):
+        if zero_before[i]:
+            k = int(g[i])
+            if k not in winners or got_ord[i] < winners[k]:
+                winners[k] = int(got_ord[i])
+    for i in range(g.size):
+        first[i] = 1 if zero_before[i] and winners[int(g[i])] == int(got_ord[i]) else 0
+    flags = rt.back(handle, torch.from_numpy(first)).numpy().reshape(-1, T)
+    is_new = flags.max(axis=1) if vals.size else np.zeros(0, dtype=np.uint8)
+    # the oracle: every rank's hashes in rank order, one at a time
+    all_vals = [None] * world
+    dist.all_gather_object(all_vals, vals.tobytes())
+    want_new = []
+    for q in range(world):
+        v = np.frombuffer(all_vals[q], dtype=np.uint64)
+        flags_q = np.array([ref.insert(int(h)) for h in v], dtype=np.uint8)
+        if q == rank:
+            want_new = flags_q
+    ok = ok and np.array_equal(is_new, want_new)
+    ref.close()
+    flag = torch.tensor([1 if ok else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("shard_worker cpu_route kind=%d world=%d: %s" % (kind, world, "routes exact" if int(flag.item()) else "MISMATCH"))
+    dist.destroy_process_group()
+    return 0 if int(flag.item()) else 1
+
+
 def main():
     mode, kind = sys.argv[1], int(sys.argv[2])
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -69,6 +161,8 @@ def main():
     budget = max(1024, per * 100 * int(os.environ.get("SHARD_BUDGET_X", "3")))
     slice_log2 = int(os.environ.get("SHARD_SLICE_LOG2", "10"))
 
+    if mode == "cpu_route":
+        return route_mode(kind, rank, world, K, sizes, bases, offsets, my_b, my_o, budget, slice_log2)
     if mode == "cpu":
         dist.init_process_group("gloo", rank=rank, world_size=world)
         plan = ShardPlan(kind, sizes, world, budget, slice_log2)
@@ -211,6 +305,31 @@ def main():
             print("rank %d: routed query differs (%d of %d)" % (rank, int((got_q != want_q).sum()), want_q.size))
             parts = [p[:0] for p in parts]  # forces a mismatch on rank 0
         ref_q.close()
+        # tracked inserts on the sharded tables (the n_unique reverse route): per-read n_new under the serial rule, ranks in
+        # order == the oracle's one-at-a-time loop over the whole read set; then OXLI save / load of the whole storage
+        saved_parts = parts
+        st.reset()
+        nk_t, n_new = st.insert_sequences_tracked(_capi.SHIFTER_CAN, K, my_b, my_o)
+        ref_t = Port(kind, 1, K, sizes)
+        _, _, want_new = ref_t.insert_reads(bases, offsets, want_n_new=True)
+        good = nk_t == (my_o.size - 1) * (100 - K + 1) and np.array_equal(n_new, want_new[r0:r1])
+        good = good and st.n_unique_kmers() == ref_t.stats()[0]
+        fn = os.path.join(os.environ.get("SHARD_TMP", "/tmp"), "shard_%d_%d.oxli" % (kind, world))
+        st.save(fn, K)
+        if rank == 0:
+            ref_t.save(fn + ".ref")
+            good = good and open(fn, "rb").read() == open(fn + ".ref", "rb").read()
+        one_pass = st.local_tables()
+        st.reset()
+        good = good and st.load(fn) == K
+        good = good and all(np.array_equal(a, b) for a, b in zip(st.local_tables(), one_pass))
+        q1 = st.query_sequences(_capi.SHIFTER_CAN, K, q_b, q_o)
+        good = good and np.array_equal(q1, ref_t.query_reads(q_b, q_o))
+        if not good:
+            print("rank %d: tracked insert / save / load check failed" % rank)
+            saved_parts = [p[:0] for p in saved_parts]
+        parts = saved_parts
+        ref_t.close()
         st.close()
 
     # gather the parts on rank 0 and compare with the oracle

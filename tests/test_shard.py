@@ -113,6 +113,16 @@ def test_peer_layout_gloo(kind, world):
     assert "tables bit-exact" in outs[0]
 
 
+@pytest.mark.parametrize("kind", [0, 1, 2])
+@pytest.mark.parametrize("world", [2, 3])
+def test_owner_routed_requests_gloo(kind, world):
+    """ShardRouter (route / ship / back) on CPU: routed queries and the first-toucher flags of a tracked insert equal the
+    oracle's serial answers; a request that reaches a rank not holding its slot fails the run."""
+    rcs, outs = launch("cpu_route", kind, world, {"SHARD_READS": "120"})
+    assert rcs == [0] * world, "\n".join(outs)
+    assert "routes exact" in outs[0]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("transport", ["p2p", "nccl"])
 @pytest.mark.parametrize("kind", [0, 1, 2])
