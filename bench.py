@@ -335,9 +335,9 @@ def main():
     L.gt_synchronize()
     launches = int(L.gt_launch_count() - launches0)
     clocks = sampler.stop()
-    prof_ms = np.zeros(3, dtype=np.float64)
-    prof_n = np.zeros(3, dtype=np.uint64)
-    _capi.check(L.gt_profile_get(prof_ms.ctypes.data, prof_n.ctypes.data), "gt_profile_get")
+    prof_ms = np.zeros(5, dtype=np.float64)
+    prof_n = np.zeros(5, dtype=np.uint64)
+    _capi.check(L.gt_profile_get_detail(prof_ms.ctypes.data, prof_n.ctypes.data, 5), "gt_profile_get_detail")
     L.gt_profile_enable(0)
     value = kmers_per_step * args.steps / (ms / 1e3)
 
@@ -462,7 +462,7 @@ def insert_roofline(prof_ms, prof_n, step_ms_total, kmers, n_tables, peak, peak_
     bytes ncu measured for one launch pair (profiles/traffic.json) -- far below the algorithmic bytes, which is
     the point of write-combining and why `frac` can exceed 1: the limiters are instruction issue (k_bucket) and
     L2 atomic throughput (k_apply), see `dram_frac` and DESIGN.md section 3."""
-    names = ("k_bucket", "k_apply (k_rebucket + k_apply_win)", "k_walk")
+    names = ("k_bucket", "k_apply (k_rebucket + k_apply_win)", "k_walk", "k_rebucket", "k_apply_win")
     algo_bytes = ALGO_BYTES_PER_KMER_PER_TABLE * n_tables
     combined = bool(prof_n[1])
     achieved = kmers * algo_bytes / (step_ms_total / 1e3) / 1e9 if step_ms_total > 0 else 0.0
@@ -540,8 +540,8 @@ def query_arm(args, torch, gb, _capi, L, dev, local_rank, storage, graph, subs, 
     L.gt_synchronize()
     launches = int(L.gt_launch_count() - launches0)
     clocks = sampler.stop()
-    prof_ms, prof_n = np.zeros(3, dtype=np.float64), np.zeros(3, dtype=np.uint64)
-    _capi.check(L.gt_profile_get(prof_ms.ctypes.data, prof_n.ctypes.data), "gt_profile_get")
+    prof_ms, prof_n = np.zeros(5, dtype=np.float64), np.zeros(5, dtype=np.uint64)
+    _capi.check(L.gt_profile_get_detail(prof_ms.ctypes.data, prof_n.ctypes.data, 5), "gt_profile_get_detail")
     L.gt_profile_enable(0)
     value = kmers_per_step * args.steps / (ms / 1e3)
     check["all_reads_pass_cutoff_1"] = bool(all(int(dp.sum().item()) == n for dp, (_, n) in zip(d_pass, subs)))
@@ -734,8 +734,8 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
     ms = float(t.item())
     launches = int(L.gt_launch_count() - launches0)
     clocks = sampler.stop()
-    prof_ms, prof_n = np.zeros(3, dtype=np.float64), np.zeros(3, dtype=np.uint64)
-    _capi.check(L.gt_profile_get(prof_ms.ctypes.data, prof_n.ctypes.data), "gt_profile_get")
+    prof_ms, prof_n = np.zeros(5, dtype=np.float64), np.zeros(5, dtype=np.uint64)
+    _capi.check(L.gt_profile_get_detail(prof_ms.ctypes.data, prof_n.ctypes.data, 5), "gt_profile_get_detail")
     L.gt_profile_enable(0)
     kmers_per_step = total_reads * kpr
     value = kmers_per_step * args.steps / (ms / 1e3)
@@ -860,7 +860,7 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
                          "algorithmic_bytes_per_kmer": algo_bytes,
                          "kernels": {name: {"launches": int(prof_n[i]), "ms_total": float(prof_ms[i]),
                                             "share_of_step": float(prof_ms[i] / ms) if ms > 0 else 0.0}
-                                     for i, name in enumerate(("k_bucket", "k_apply")) if prof_n[i]}},
+                                     for i, name in enumerate(("k_bucket", "k_apply", "k_walk", "k_rebucket", "k_apply_win")) if prof_n[i]}},
             "nvlink": nvlink_report(nv0, nv1, kmers_rank * args.steps, n_tables, world, ms, peer_bytes),
             "cpu_baseline": None,
             "check": check,

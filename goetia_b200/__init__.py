@@ -14,5 +14,6 @@ from .dbg import dBG  # noqa: F401
 from .sketch import SourmashSketch  # noqa: F401
 from .parsing import FastxParser, Record, SplitPairedReader  # noqa: F401
 from .filters import DiginormFilter, FilterProcessor, StreamingSolidFilter  # noqa: F401
+from .processors import InserterProcessor  # noqa: F401
 
 __version__ = "0.1.0"

@@ -110,6 +110,7 @@ SIGNATURES = {
     "gt_timer_elapsed_ms": (C.c_double, [C.c_int, C.c_int]),
     "gt_profile_enable": (C.c_int, [C.c_int]),
     "gt_profile_get": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gt_profile_get_detail": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "gt_fastx_open": (C.c_void_p, [C.c_char_p, C.c_int, C.c_uint32]),
     "gt_fastx_close": (None, [C.c_void_p]),
     "gt_fastx_next_record": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -117,6 +118,7 @@ SIGNATURES = {
     "gt_fastx_next_batch": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
     "gt_fastx_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gt_insert_fastx": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint64, C.c_void_p]),
+    "gt_insert_fastx_advance": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]),
     "gt_max_hash_from_scaled": (C.c_uint64, [C.c_uint64]),
     "gt_sketch_create": (C.c_void_p, [C.c_uint32, C.c_int, C.c_uint32, C.c_uint64]),
     "gt_sketch_destroy": (None, [C.c_void_p]),

@@ -639,6 +639,200 @@ k_rebucket(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ it
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// k_rebucket2: the same partition by STAGING ROWS (as k_bucket does at level 1) instead of a counting sort.
+//
+// k_rebucket above is bound by shared-memory wavefronts and barriers (ncu, profiles/r2_ncu_full_v1.txt: 16
+// wavefronts per warp and entry -- histogram atomic, rank lookup, scatter, gather, base lookup -- and six barriers
+// per 8192 entries; 10.4 ms per 2.9 G entries against 3.7 ms for its 24 GB of DRAM traffic).  Here a persistent
+// CTA keeps one row of C entries per window in shared memory; an entry costs ONE returning shared atomic (the
+// row cursor) and ONE shared store.  After every 8192-entry chunk each row is sent to its sub-bucket by its owner
+// thread: one global cursor reservation and ONE bulk (TMA) copy shared -> global of the row's multiple-of-4
+// prefix; the 0..3 entries behind it move to the front of the row (one 16-byte load and store) and go out with
+// the next chunk, so sub-buckets hold no pad entries except where a CTA leaves a slice (rows are then padded to
+// 16 bytes and emptied).  The chunks of an item are dealt round-robin to the CTAs, item after item: all CTAs work
+// on the same slice at about the same time, so the slice's n_win output streams stay together in DRAM; the next
+// chunk is loaded into registers while the current one is staged.  A row that is full (skewed input) and a
+// sub-bucket that is full send the update straight to the table, as k_rebucket does.
+// shared memory: cnt[nw_max + 1] (cnt[nw_max]: where pad entries count themselves) | stage[nw_max][C]
+// C/4 is odd: consecutive rows then start 4 banks apart modulo 32 (a multiple of 8 would put all rows on 2 or 4
+// bank groups: rows fill at the same pace, so the append positions of a warp would collide).
+// ------------------------------------------------------------------------------------------
+constexpr int RB2_THREADS = 512;
+constexpr int RB2_PER_THREAD = AP_CHUNK / RB2_THREADS;  // 16
+constexpr int RB2_ROWS_PER_PASS = RB2_THREADS / 4;  // a flush handles the rows in passes of 128: 4 lanes per row
+
+// this CTA's walk over the chunks: item after item, chunk j of an item goes to CTA (chunks of earlier items + j) % grid
+struct ChunkWalk {
+    const ApplyItem* items;
+    int n_items, b, ips, slice;
+    uint32_t j, nch, rot, fill;
+    const uint32_t* src;
+    __device__ __forceinline__ void open_item() {  // b is valid: read its fill, find this CTA's first chunk in it
+        const ApplyItem it = items[b];
+        fill = min(__ldcg(it.fill), it.cap);
+        src = it.src;
+        nch = (fill + (uint32_t)AP_CHUNK - 1) / (uint32_t)AP_CHUNK;
+        j = (blockIdx.x + gridDim.x - rot) % gridDim.x;
+        slice = b / ips;
+    }
+    __device__ __forceinline__ void start(const ApplyItem* items_, int n_items_, int ips_) {
+        items = items_; n_items = n_items_; ips = ips_; b = 0; slice = 0; rot = 0; j = nch = fill = 0; src = nullptr;
+        if (n_items > 0) { open_item(); settle(); }
+    }
+    __device__ __forceinline__ void settle() {  // move on to the next item until this CTA has a chunk in it
+        while (b < n_items && j >= nch) {
+            rot = (rot + nch) % gridDim.x;
+            if (++b < n_items) open_item();
+        }
+    }
+    __device__ __forceinline__ bool done() const { return b >= n_items; }
+    __device__ __forceinline__ void next() { j += gridDim.x; settle(); }
+};
+
+__device__ __forceinline__ void rb2_load(const ChunkWalk& w, uint32_t (&v)[RB2_PER_THREAD], int tid) {
+    const uint32_t e0 = w.j * (uint32_t)AP_CHUNK;
+    const uint32_t n = min((uint32_t)AP_CHUNK, w.fill - e0);
+    const uint32_t* src = w.src + e0;
+    if (n == AP_CHUNK && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+#pragma unroll
+        for (int k = 0; k < RB2_PER_THREAD / 4; ++k) {
+            const uint4 x = __ldcs(reinterpret_cast<const uint4*>(src) + k * RB2_THREADS + tid);
+            v[4 * k] = x.x; v[4 * k + 1] = x.y; v[4 * k + 2] = x.z; v[4 * k + 3] = x.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < RB2_PER_THREAD; ++k) {
+            const uint32_t e = (uint32_t)k * RB2_THREADS + tid;
+            v[k] = e < n ? __ldcs(src + e) : BK_PAD;
+        }
+    }
+}
+
+template <int KIND, int PASSES>  // PASSES * 128 >= windows per slice
+__global__ void __launch_bounds__(RB2_THREADS, 2)
+k_rebucket2(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ items, int n_items, int items_per_slice,
+            const SliceWin* __restrict__ slices, int wshift, int nw_max, uint32_t C, uint32_t wmask, uint32_t stage_off) {
+    // wmask = 2^wshift - 1 and stage_off = (nw_max + 4) & ~3 come as parameters: constant-bank operands cost no
+    // registers, and the compiler otherwise re-derives them inside the predicated append (64-register budget)
+    extern __shared__ __align__(16) uint32_t rb_sm[];
+    uint32_t* cnt = rb_sm;                    // [nw_max + 1], padded to a multiple of 4 words
+    uint32_t* stage = rb_sm + stage_off;
+    const int tid = threadIdx.x;
+    for (int w = tid; w < nw_max; w += RB2_THREADS) cnt[w] = 0;
+    // pads count themselves in cnt[nw_max], which starts at 2^31: their index is never < C (no store) and, read as a
+    // signed number, never >= C (no overflow flag)
+    if (tid == 0) cnt[nw_max] = 0x80000000u;
+    __syncthreads();
+    const uint32_t nwm = (uint32_t)nw_max;
+    int cur_slice = -1;
+    SliceWin sl;
+    uint32_t* tbl = nullptr;
+
+    // Send the rows out: 4 lanes per row, 128 rows per pass.  The group's first lane takes the row's multiple-of-4
+    // prefix, reserves room in the sub-bucket (all passes' reservations are issued before any is waited for), the four
+    // lanes copy it with 16-byte loads and stores, and the 0..3 entries behind it move to the front of the row.
+    // (A bulk copy per row would cost more here: UBLKCP is a uniform-datapath instruction, so per-lane copies are
+    // serialised by a ~10-instruction loop per lane -- 2 G of the 4.7 G warp instructions of the first version.)
+    // final: the CTA leaves the slice -- rows are padded to 16 bytes and emptied.
+    auto flush = [&](bool final) {
+        const int q = tid & 3, lead = tid & 28;
+        const uint32_t C4 = C >> 2;
+        uint4* stage16 = reinterpret_cast<uint4*>(stage);
+        uint32_t g_[PASSES], n4_[PASSES];
+#pragma unroll
+        for (int i = 0; i < PASSES; ++i) {
+            const uint32_t row = (uint32_t)(tid >> 2) + i * RB2_ROWS_PER_PASS;
+            uint32_t n4 = 0, g = 0;
+            if (q == 0 && row < sl.n_win) {
+                const uint32_t n = min(cnt[row], C);
+                n4 = n & ~3u;
+                if (final && n4 != n) {
+                    uint32_t* r = stage + (size_t)row * C;
+                    for (uint32_t e = n; e < n4 + 4; ++e) r[e] = BK_PAD;  // C is a multiple of 4
+                    n4 += 4;
+                }
+                cnt[row] = final ? 0u : n - n4;
+                if (n4) g = atomicAdd(sl.sub_fill + row, n4);
+            }
+            g_[i] = g;
+            n4_[i] = n4;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < PASSES; ++i) {
+            const uint32_t row = (uint32_t)(tid >> 2) + i * RB2_ROWS_PER_PASS;
+            const uint32_t n4 = __shfl_sync(0xffffffffu, n4_[i], lead), g = __shfl_sync(0xffffffffu, g_[i], lead);
+            if (n4) {
+                uint4* r16 = stage16 + (size_t)row * C4;
+                uint32_t* dst = sl.sub + (size_t)row * sl.cap2;
+                if (g + n4 <= sl.cap2) {
+                    uint4* d16 = reinterpret_cast<uint4*>(dst + g);
+                    for (uint32_t u = q; u < (n4 >> 2); u += 4) d16[u] = r16[u];
+                } else if (q == 0) {  // sub-bucket full (skewed input): what does not fit goes straight to the table
+                    const uint32_t* r = stage + (size_t)row * C;
+                    for (uint32_t e = 0; e < n4; ++e) {
+                        const uint32_t x = r[e];
+                        if (g + e < sl.cap2) dst[g + e] = x;
+                        else if (x != BK_PAD) slot_insert<KIND, false>(tbl, ((uint64_t)row << wshift) + x);
+                    }
+                }
+            }
+            __syncwarp();
+            if (!final && n4 && n4 < C) {  // one word per lane: the row's first granule <- the granule behind the prefix
+                uint32_t* r = stage + (size_t)row * C;
+                r[q] = r[n4 + q];
+            }
+        }
+    };
+
+    ChunkWalk cw;
+    cw.start(items, n_items, items_per_slice);
+    uint32_t v[RB2_PER_THREAD], nx[RB2_PER_THREAD];
+    if (!cw.done()) rb2_load(cw, nx, tid);
+    while (!cw.done()) {
+        const int s = cw.slice;
+        if (s != cur_slice) {
+            if (cur_slice >= 0) {
+                flush(true);
+                __syncthreads();
+            }
+            cur_slice = s;
+            sl = slices[s];
+            tbl = slice_words_ptr<KIND>(ts, sl.table, sl.slot0);
+        }
+#pragma unroll
+        for (int k = 0; k < RB2_PER_THREAD; ++k) v[k] = nx[k];
+        cw.next();
+        if (!cw.done()) rb2_load(cw, nx, tid);  // in flight while this chunk is staged
+        uint32_t ovf = 0;
+#pragma unroll
+        for (int k0 = 0; k0 < RB2_PER_THREAD; k0 += 4) {  // four row cursors in flight before the first store needs one
+            uint32_t w[4], idx[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                w[k] = min(v[k0 + k] >> wshift, nwm);  // pads (0xFFFFFFFF) go to cnt[nw_max]
+                idx[k] = atomicAdd(&cnt[w[k]], 1u);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (idx[k] < C) stage[w[k] * C + idx[k]] = v[k0 + k] & wmask;
+                if ((int32_t)idx[k] >= (int32_t)C) ovf |= 1u << (k0 + k);
+            }
+        }
+        if (ovf) {  // row full (skewed input): straight to the table
+#pragma unroll
+            for (int k = 0; k < RB2_PER_THREAD; ++k)
+                if (ovf & (1u << k)) slot_insert<KIND, false>(tbl, v[k]);
+        }
+        fence_async_smem();
+        __syncthreads();
+        flush(false);
+        __syncthreads();
+    }
+    if (cur_slice >= 0) flush(true);
+}
+
 template <int KIND>
 __device__ __forceinline__ void window_update(uint32_t* __restrict__ win, uint32_t off) {
     if constexpr (KIND == 0) {

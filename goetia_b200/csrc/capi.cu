@@ -110,13 +110,13 @@ static unsigned long long g_launches = 0;  // kernels of this library launched s
 
 // Optional per-kernel device timing (gt_profile_*): CUDA event pairs around the launches of the
 // two insert kernels on the stream they run on; resolved lazily.  Off by default.
-enum { PROF_BUCKET = 0, PROF_APPLY = 1, PROF_WALK = 2, PROF_KINDS = 3 };
+enum { PROF_BUCKET = 0, PROF_APPLY = 1, PROF_WALK = 2, PROF_REBUCKET = 3, PROF_APPLY_WIN = 4, PROF_KINDS = 5 };  // 3, 4: inside PROF_APPLY
 struct ProfSpan { cudaEvent_t a, b; int kind; };
 static bool g_prof_on = false;
 static std::vector<ProfSpan> g_prof_open;
 static std::vector<cudaEvent_t> g_prof_pool;
-static double g_prof_ms[PROF_KINDS] = {0, 0, 0};
-static unsigned long long g_prof_n[PROF_KINDS] = {0, 0, 0};
+static double g_prof_ms[PROF_KINDS] = {0};
+static unsigned long long g_prof_n[PROF_KINDS] = {0};
 static cudaEvent_t prof_event() {
     cudaEvent_t e = nullptr;
     if (!g_prof_pool.empty()) { e = g_prof_pool.back(); g_prof_pool.pop_back(); }
@@ -1807,8 +1807,16 @@ extern "C" int gt_profile_get(double* ms3, uint64_t* n3) {
     if (!ms3 || !n3) return fail("gt_profile_get: NULL argument");
     CU(cudaDeviceSynchronize());
     prof_resolve();
-    for (int k = 0; k < PROF_KINDS; ++k) { ms3[k] = g_prof_ms[k]; n3[k] = g_prof_n[k]; }
+    for (int k = 0; k < 3; ++k) { ms3[k] = g_prof_ms[k]; n3[k] = g_prof_n[k]; }
     return 0;
+}
+extern "C" int gt_profile_get_detail(double* ms, uint64_t* n, int count) {
+    if (ensure_ctx()) return -1;
+    if (!ms || !n || count < 0) return fail("gt_profile_get_detail: bad argument");
+    CU(cudaDeviceSynchronize());
+    prof_resolve();
+    for (int k = 0; k < count; ++k) { ms[k] = k < PROF_KINDS ? g_prof_ms[k] : 0.0; n[k] = k < PROF_KINDS ? g_prof_n[k] : 0; }
+    return PROF_KINDS;
 }
 
 // exclusive scan of per-read k-mer counts on stream s

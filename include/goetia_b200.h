@@ -258,6 +258,9 @@ double gt_timer_elapsed_ms(int from_slot, int to_slot);
  * ms3/n3 = {k_bucket, k_apply, k_walk} accumulated since gt_profile_enable(1). */
 int gt_profile_enable(int on);
 int gt_profile_get(double* ms3, uint64_t* n3);
+/* The same with the apply split up: ms/n[0..count) = {k_bucket, apply (whole), k_walk, k_rebucket, k_apply_win};
+ * returns the number of kinds the library tracks. */
+int gt_profile_get_detail(double* ms, uint64_t* n, int count);
 
 /* ---- sharded storage: one process per GPU (no counterpart in the reference) -------------- */
 /* Table t is cut into slices of 2^shift slots; rank r of `world` holds a contiguous run of
@@ -393,6 +396,13 @@ int gt_fastx_stats(const gt_fastx* fx, uint64_t* n_parsed, uint64_t* n_skipped, 
  * SequenceLengthException). */
 int64_t gt_insert_fastx(gt_storage* st, int shifter, int K, gt_fastx* fx, int mode, uint64_t max_reads,
                         uint64_t* n_seqs);
+
+/* FileProcessor::advance (processors.hh:208-229) in the reference's own "time" unit: consume records until the k-mers
+ * processed by this call reach interval_kmers (IntervalCounter::poll, metrics.hh:129-138: the record that crosses the
+ * threshold is the last one consumed) or the file ends.  Returns the k-mers consumed; *n_seqs = records consumed;
+ * *remaining = 1 when the interval ended the call, 0 at the end of the file. */
+int64_t gt_insert_fastx_advance(gt_storage* st, int shifter, int K, gt_fastx* fx, int mode, uint64_t interval_kmers,
+                                uint64_t* n_seqs, int* remaining);
 
 /* ---- SourmashSketch (sketches/sourmash_sketch.hh:24-82) -------------------------------- */
 /* Sketch(n, K, is_protein=false, dayhoff=false, hp=false, seed, scaled):

@@ -398,6 +398,9 @@ class _RefLib:
             L.ref_dbg_load.argtypes = [C.c_void_p, C.c_char_p]
             L.ref_dbg_process_file.restype = C.c_int64
             L.ref_dbg_process_file.argtypes = [C.c_void_p, C.c_char_p, u64p, u64p]
+            if hasattr(L, "ref_dbg_advance_trace"):
+                L.ref_dbg_advance_trace.restype = C.c_int64
+                L.ref_dbg_advance_trace.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int, C.c_uint32, C.c_void_p, C.c_uint64]
             L.ref_dbg_median_count_at_least.restype = C.c_int
             L.ref_dbg_median_count_at_least.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint]
             L.ref_dbg_insert_reads.restype = C.c_int64
@@ -580,6 +583,14 @@ class Ref(_GraphBase):
         a, b = C.c_uint64(0), C.c_uint64(0)
         t = self.L.ref_dbg_process_file(self.h, fn.encode(), C.byref(a), C.byref(b))
         return int(t), int(a.value), int(b.value)
+
+    def advance_trace(self, fn, interval, strict=False, min_length=0, cap=1 << 16):
+        """FileProcessor::advance until nothing remains -> [(n_sequences, time_total, remaining), ...]."""
+        out = np.zeros((cap, 3), dtype=np.uint64)
+        n = self.L.ref_dbg_advance_trace(self.h, fn.encode(), int(interval), int(bool(strict)), int(min_length), out.ctypes.data, cap)
+        if n < 0:
+            raise ValueError("advance_trace failed")
+        return [(int(a), int(b), bool(c)) for a, b, c in out[:min(n, cap)]]
 
     def stats(self):
         a, b = C.c_uint64(0), C.c_uint64(0)

@@ -65,6 +65,8 @@ struct RefGraph {
     virtual void save(const std::string& fn) = 0;
     virtual void load(const std::string& fn) = 0;
     virtual int64_t process_file(const std::string& fn, uint64_t* n_seqs, uint64_t* n_skipped) = 0;
+    virtual int64_t advance_trace(const std::string& fn, uint64_t interval, bool strict, uint32_t min_length,
+                                  uint64_t* out, uint64_t cap) = 0;
     virtual int median_count_at_least(const std::string& s, unsigned cutoff) = 0;
     virtual int64_t insert_reads_mt(const char* bases, const uint64_t* offsets, uint64_t n_reads,
                                     int n_threads) = 0;
@@ -137,6 +139,26 @@ struct RefGraphImpl : RefGraph {
         *n_seqs = std::get<0>(res);
         *n_skipped = parser->n_skipped();
         return (int64_t)std::get<1>(res);
+    }
+    int64_t advance_trace(const std::string& fn, uint64_t interval, bool strict, uint32_t min_length,
+                          uint64_t* out, uint64_t cap) override {
+        /* FileProcessor::advance (processors.hh:208-229) called until nothing remains; every return value
+         * <n_sequences, time_total, remaining> is recorded */
+        auto proc = graph_t::Processor::build(g, interval, false);
+        auto parser = FastxParser<DNA_SIMPLE>::build(fn, strict, min_length);
+        uint64_t n = 0;
+        bool remaining = true;
+        while (remaining) {
+            auto res = proc->advance(parser);
+            remaining = std::get<2>(res);
+            if (n < cap) {
+                out[3 * n] = std::get<0>(res);
+                out[3 * n + 1] = std::get<1>(res);
+                out[3 * n + 2] = remaining ? 1 : 0;
+            }
+            ++n;
+        }
+        return (int64_t)n;
     }
     int median_count_at_least(const std::string& s, unsigned cutoff) override {
         return median_helper<S>::run(s, cutoff, *g);
@@ -225,6 +247,12 @@ int ref_dbg_load(void* p, const char* fn) {
 }
 int64_t ref_dbg_process_file(void* p, const char* fn, uint64_t* n_seqs, uint64_t* n_skipped) {
     return static_cast<RefGraph*>(p)->process_file(fn, n_seqs, n_skipped);
+}
+int64_t ref_dbg_advance_trace(void* p, const char* fn, uint64_t interval, int strict, uint32_t min_length, uint64_t* out,
+                              uint64_t cap) {
+    try {
+        return static_cast<RefGraph*>(p)->advance_trace(fn, interval, strict != 0, min_length, out, cap);
+    } catch (...) { return -1; }
 }
 int ref_dbg_median_count_at_least(void* p, const char* seq, uint64_t len, unsigned cutoff) {
     try {

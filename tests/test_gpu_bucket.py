@@ -17,16 +17,20 @@ pytestmark = pytest.mark.gpu
 
 
 # How the buckets are applied (bucket.cuh): "atomics" = k_apply (global RED / CAS per update); "win1" = k_apply_win
-# with one shared-memory window per slice; "win2" = k_rebucket into 128-byte windows + k_apply_win (two-level).
-APPLY = {"atomics": ("0", "16"), "win1": ("2", "16"), "win2": ("2", "7")}
+# with one shared-memory window per slice; "win2" = k_rebucket2 into 128-byte windows + k_apply_win (two-level);
+# "win2tiny": the same with k_rebucket2's staging rows cut to 8 entries, so that rows overflow all the time and the excess
+# takes the direct route.
+APPLY = {"atomics": ("0", "16", None), "win1": ("2", "16", None), "win2": ("2", "7", None), "win2tiny": ("2", "7", "8")}
 
 
 @pytest.fixture(params=sorted(APPLY))
 def forced(monkeypatch, request):
     """Force the bucket path with tiny slices and a tiny store (many buckets, many flushes)."""
-    mode, wlog2 = APPLY[request.param]
+    mode, wlog2, row = APPLY[request.param]
     monkeypatch.setenv("GT_APPLY_WINDOWS", mode)
     monkeypatch.setenv("GT_WINDOW_LOG2_BYTES", wlog2)
+    if row:
+        monkeypatch.setenv("GT_REBUCKET_ROW", row)
 
     def set_env(slice_log2=12, entries=1 << 20, min_kmers=0):
         monkeypatch.setenv("GT_BUCKET_FORCE", "1")
