@@ -58,7 +58,7 @@ WORKLOADS = {
     "c4": (-1, 31, 1000, 0, 100_000_000, 150, 45,
            "C4: SourmashSketch K=31 scaled=1000 streaming sketch of 100M x 150bp synthetic reads"),
 }
-SUB_BATCH_BASES = 900_000_000  # reads are fed to the library in sub-batches of about this many bases
+SUB_BATCH_BASES = int(os.environ.get("GT_BENCH_SUB_BASES", 900_000_000))  # reads are fed to the library in sub-batches of about this many bases
 
 
 def parse_args():

@@ -207,6 +207,10 @@ k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts
     uint32_t* stage = reinterpret_cast<uint32_t*>(sw + tile_words + (tile_words & 1));  // [nb][C], 16-byte aligned rows
     // cnt[2][nb]: next free staging index of every bucket, ABSOLUTE (row b starts at b * C), for this / the next sub-step
     uint32_t* cnt = stage + (size_t)nb * C;
+    // capacity and entry array of every bucket, copied here once: the copy-out reads them for every row and sub-step,
+    // and a global load there is latency nobody hides (ncu: the capacity test was the kernel's top stall line)
+    uint32_t* s_cap = cnt + 2 * nb;
+    uint32_t** s_dst = reinterpret_cast<uint32_t**>(s_cap + nb + (nb & 1));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 4) {
         tab[tid] = make_ulonglong2(lemire_T(tid), rotl64(lemire_T(3 - tid), (unsigned)K));
@@ -218,6 +222,10 @@ k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts
         tab2[tid] = make_ulonglong2(rotl1(lemire_T(c0)) ^ lemire_T(c1), lemire_T(3 - c0) ^ rotl1(lemire_T(3 - c1)));
     }
     for (int b = tid; b < 2 * nb; b += TILE_THREADS) cnt[b] = (uint32_t)(b < nb ? b : b - nb) * C;
+    for (int b = tid; b < nb; b += TILE_THREADS) {
+        s_cap[b] = __ldg(bp.bcap + b);
+        s_dst[b] = bp.bptr[b];
+    }
     const uint64_t n_tiles = (a.n_bases + TILE_POS - 1) / TILE_POS;
     const uint32_t slot_mask = (uint32_t)((1ull << bp.shift) - 1);
     unsigned long long direct = 0, dropped = 0;
@@ -317,6 +325,7 @@ k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts
                     }
                     if (rok && p + (uint64_t)K <= rend) {
                         const uint64_t h = CAN ? (fw < rc ? fw : rc) : fw;  // Canonical::value(), canonical.hh:124-126
+                        uint32_t full = 0;  // tables whose row was full (skewed input): handled behind the loop, off the hot path
 #pragma unroll
                         for (int t = 0; t < nt; ++t) {
                             const uint64_t bin = bin_of_t<BIG>(h, ts, bp, t);
@@ -324,7 +333,14 @@ k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts
                             const uint32_t off = (uint32_t)bin & slot_mask;
                             const uint32_t idx = atomicAdd(&cn[b], 1u);  // absolute staging index
                             if (idx < b * C + C) stage[idx] = off;
-                            else bucket_spill<KIND>(ts, bp, t, b, off, direct, dropped);
+                            else full |= 1u << t;
+                        }
+                        if (full) {
+                            for (int t = 0; t < nt; ++t) {
+                                if (!((full >> t) & 1u)) continue;
+                                const uint64_t bin = bin_of_t<BIG>(h, ts, bp, t);
+                                bucket_spill<KIND>(ts, bp, t, bp.first[t] + (uint32_t)(bin >> bp.shift), (uint32_t)bin & slot_mask, direct, dropped);
+                            }
                         }
                     }
                 }
@@ -367,8 +383,8 @@ k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts
                     }
                     if (c_left[rr] < C4 && c_nxt[rr] == BK_NONE) c_nxt[rr] = atomicAdd(bp.bfill + mine, R);
                 }
-                const uint32_t cap = __ldg(bp.bcap + mine);
-                uint32_t* dst = bp.bptr[mine];
+                const uint32_t cap = s_cap[mine];
+                uint32_t* dst = s_dst[mine];
                 if ((l0 == 0 || d0 + l0 <= cap) && (l1 == 0 || d1 + l1 <= cap)) {
                     fence_async_smem();  // the pad entries above
                     if (l0) bulk_row_out(dst + d0, row, l0 * 4u);
@@ -409,8 +425,8 @@ k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts
         for (int rr = 0; rr < BK_OWN; ++rr) {
             const int mine = warp + rr * TILE_THREADS + 8 * lane;
             if (mine >= nb) continue;
-            const uint32_t cap = __ldg(bp.bcap + mine);
-            uint32_t* dst = bp.bptr[mine];
+            const uint32_t cap = s_cap[mine];
+            uint32_t* dst = s_dst[mine];
             const uint4 pad = make_uint4(BK_PAD, BK_PAD, BK_PAD, BK_PAD);
             for (uint32_t e = c_pos[rr]; e < c_pos[rr] + c_left[rr] && e < cap; e += 4) *reinterpret_cast<uint4*>(dst + e) = pad;
             if (c_nxt[rr] != BK_NONE)
@@ -646,7 +662,7 @@ k_rebucket(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ it
 // wavefronts per warp and entry -- histogram atomic, rank lookup, scatter, gather, base lookup -- and six barriers
 // per 8192 entries; 10.4 ms per 2.9 G entries against 3.7 ms for its 24 GB of DRAM traffic).  Here a persistent
 // CTA keeps one row of C entries per window in shared memory; an entry costs ONE returning shared atomic (the
-// row cursor) and ONE shared store.  After every 8192-entry chunk each row is sent to its sub-bucket by its owner
+// row cursor) and ONE shared store.  After every chunk (16 entries per thread) each row is sent to its sub-bucket by its owner
 // thread: one global cursor reservation and ONE bulk (TMA) copy shared -> global of the row's multiple-of-4
 // prefix; the 0..3 entries behind it move to the front of the row (one 16-byte load and store) and go out with
 // the next chunk, so sub-buckets hold no pad entries except where a CTA leaves a slice (rows are then padded to
@@ -658,26 +674,24 @@ k_rebucket(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ it
 // C/4 is odd: consecutive rows then start 4 banks apart modulo 32 (a multiple of 8 would put all rows on 2 or 4
 // bank groups: rows fill at the same pace, so the append positions of a warp would collide).
 // ------------------------------------------------------------------------------------------
-constexpr int RB2_THREADS = 512;
-constexpr int RB2_PER_THREAD = AP_CHUNK / RB2_THREADS;  // 16
-constexpr int RB2_ROWS_PER_PASS = RB2_THREADS / 4;  // a flush handles the rows in passes of 128: 4 lanes per row
+constexpr int RB2_PER_THREAD = 16;  // entries a thread stages per chunk: a chunk is T * 16 entries (T threads per CTA)
 
 // this CTA's walk over the chunks: item after item, chunk j of an item goes to CTA (chunks of earlier items + j) % grid
 struct ChunkWalk {
     const ApplyItem* items;
     int n_items, b, ips, slice;
-    uint32_t j, nch, rot, fill;
+    uint32_t j, nch, rot, fill, chunk;
     const uint32_t* src;
     __device__ __forceinline__ void open_item() {  // b is valid: read its fill, find this CTA's first chunk in it
         const ApplyItem it = items[b];
         fill = min(__ldcg(it.fill), it.cap);
         src = it.src;
-        nch = (fill + (uint32_t)AP_CHUNK - 1) / (uint32_t)AP_CHUNK;
+        nch = (fill + chunk - 1) / chunk;
         j = (blockIdx.x + gridDim.x - rot) % gridDim.x;
         slice = b / ips;
     }
-    __device__ __forceinline__ void start(const ApplyItem* items_, int n_items_, int ips_) {
-        items = items_; n_items = n_items_; ips = ips_; b = 0; slice = 0; rot = 0; j = nch = fill = 0; src = nullptr;
+    __device__ __forceinline__ void start(const ApplyItem* items_, int n_items_, int ips_, uint32_t chunk_) {
+        chunk = chunk_; items = items_; n_items = n_items_; ips = ips_; b = 0; slice = 0; rot = 0; j = nch = fill = 0; src = nullptr;
         if (n_items > 0) { open_item(); settle(); }
     }
     __device__ __forceinline__ void settle() {  // move on to the next item until this CTA has a chunk in it
@@ -690,27 +704,28 @@ struct ChunkWalk {
     __device__ __forceinline__ void next() { j += gridDim.x; settle(); }
 };
 
+template <int T>
 __device__ __forceinline__ void rb2_load(const ChunkWalk& w, uint32_t (&v)[RB2_PER_THREAD], int tid) {
-    const uint32_t e0 = w.j * (uint32_t)AP_CHUNK;
-    const uint32_t n = min((uint32_t)AP_CHUNK, w.fill - e0);
+    const uint32_t e0 = w.j * w.chunk;
+    const uint32_t n = min(w.chunk, w.fill - e0);
     const uint32_t* src = w.src + e0;
-    if (n == AP_CHUNK && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+    if (n == w.chunk && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
 #pragma unroll
         for (int k = 0; k < RB2_PER_THREAD / 4; ++k) {
-            const uint4 x = __ldcs(reinterpret_cast<const uint4*>(src) + k * RB2_THREADS + tid);
+            const uint4 x = __ldcs(reinterpret_cast<const uint4*>(src) + k * T + tid);
             v[4 * k] = x.x; v[4 * k + 1] = x.y; v[4 * k + 2] = x.z; v[4 * k + 3] = x.w;
         }
     } else {
 #pragma unroll
         for (int k = 0; k < RB2_PER_THREAD; ++k) {
-            const uint32_t e = (uint32_t)k * RB2_THREADS + tid;
+            const uint32_t e = (uint32_t)k * T + tid;
             v[k] = e < n ? __ldcs(src + e) : BK_PAD;
         }
     }
 }
 
-template <int KIND, int PASSES>  // PASSES * 128 >= windows per slice
-__global__ void __launch_bounds__(RB2_THREADS, 2)
+template <int KIND, int T, int PASSES>  // T threads; PASSES * T / 4 >= windows per slice
+__global__ void __launch_bounds__(T, 1024 / T)
 k_rebucket2(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ items, int n_items, int items_per_slice,
             const SliceWin* __restrict__ slices, int wshift, int nw_max, uint32_t C, uint32_t wmask, uint32_t stage_off) {
     // wmask = 2^wshift - 1 and stage_off = (nw_max + 4) & ~3 come as parameters: constant-bank operands cost no
@@ -719,7 +734,7 @@ k_rebucket2(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ i
     uint32_t* cnt = rb_sm;                    // [nw_max + 1], padded to a multiple of 4 words
     uint32_t* stage = rb_sm + stage_off;
     const int tid = threadIdx.x;
-    for (int w = tid; w < nw_max; w += RB2_THREADS) cnt[w] = 0;
+    for (int w = tid; w < nw_max; w += T) cnt[w] = 0;
     // pads count themselves in cnt[nw_max], which starts at 2^31: their index is never < C (no store) and, read as a
     // signed number, never >= C (no overflow flag)
     if (tid == 0) cnt[nw_max] = 0x80000000u;
@@ -742,7 +757,7 @@ k_rebucket2(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ i
         uint32_t g_[PASSES], n4_[PASSES];
 #pragma unroll
         for (int i = 0; i < PASSES; ++i) {
-            const uint32_t row = (uint32_t)(tid >> 2) + i * RB2_ROWS_PER_PASS;
+            const uint32_t row = (uint32_t)(tid >> 2) + i * (T / 4);
             uint32_t n4 = 0, g = 0;
             if (q == 0 && row < sl.n_win) {
                 const uint32_t n = min(cnt[row], C);
@@ -761,7 +776,7 @@ k_rebucket2(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ i
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < PASSES; ++i) {
-            const uint32_t row = (uint32_t)(tid >> 2) + i * RB2_ROWS_PER_PASS;
+            const uint32_t row = (uint32_t)(tid >> 2) + i * (T / 4);
             const uint32_t n4 = __shfl_sync(0xffffffffu, n4_[i], lead), g = __shfl_sync(0xffffffffu, g_[i], lead);
             if (n4) {
                 uint4* r16 = stage16 + (size_t)row * C4;
@@ -787,9 +802,9 @@ k_rebucket2(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ i
     };
 
     ChunkWalk cw;
-    cw.start(items, n_items, items_per_slice);
+    cw.start(items, n_items, items_per_slice, (uint32_t)T * RB2_PER_THREAD);
     uint32_t v[RB2_PER_THREAD], nx[RB2_PER_THREAD];
-    if (!cw.done()) rb2_load(cw, nx, tid);
+    if (!cw.done()) rb2_load<T>(cw, nx, tid);
     while (!cw.done()) {
         const int s = cw.slice;
         if (s != cur_slice) {
@@ -804,7 +819,7 @@ k_rebucket2(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ i
 #pragma unroll
         for (int k = 0; k < RB2_PER_THREAD; ++k) v[k] = nx[k];
         cw.next();
-        if (!cw.done()) rb2_load(cw, nx, tid);  // in flight while this chunk is staged
+        if (!cw.done()) rb2_load<T>(cw, nx, tid);  // in flight while this chunk is staged
         uint32_t ovf = 0;
 #pragma unroll
         for (int k0 = 0; k0 < RB2_PER_THREAD; k0 += 4) {  // four row cursors in flight before the first store needs one
