@@ -47,8 +47,10 @@ struct ProducePlan {
     // cheap exact h % size for tables of >= 2^28 slots (see bin_of): dsh = size << rs >= 2^32,
     // m32 = floor((2^64-1) / dsh) < 2^32; rs < 0 selects the generic 64-bit fastmod
     uint64_t dsh[MAX_TABLES];
+    uint64_t negd[MAX_TABLES];        // 2^64 - dsh: h - q * d is one multiply-add on h + q * negd
     uint32_t m32[MAX_TABLES];
     int32_t rs[MAX_TABLES];
+    uint32_t slot_mask;               // 2^shift - 1
     uint32_t stage_cap;               // shared-memory staging entries per bucket and sub-step (multiple of 4)
     uint32_t piece;                   // entries a CTA takes from a bucket's cursor at a time (0: exact-size requests)
     uint32_t* const* bptr;            // [n_buckets] entry array of each bucket
@@ -179,11 +181,12 @@ template <bool BIG>
 __device__ __forceinline__ uint64_t bin_of_t(uint64_t h, const TableSet& ts, const ProducePlan& bp, int t) {
     if constexpr (BIG) {
         const uint64_t d = bp.dsh[t];  // == ts.size[t]
+        const uint64_t nd = bp.negd[t];
         const uint32_t m = bp.m32[t];
         const uint32_t q = (uint32_t)(((uint64_t)(uint32_t)(h >> 32) * m + __umulhi((uint32_t)h, m)) >> 32);
-        const uint64_t ql = (uint64_t)q * (uint32_t)d;
-        const uint32_t qh = (uint32_t)(ql >> 32) + q * (uint32_t)(d >> 32);
-        const uint64_t r = h - (((uint64_t)qh << 32) | (uint32_t)ql);  // < 2 d
+        // h - q * d = h + q * (2^64 - d) modulo 2^64: one wide multiply-add and one 32-bit one
+        const uint64_t lo = (uint64_t)q * (uint32_t)nd + h;
+        const uint64_t r = lo + ((uint64_t)(q * (uint32_t)(nd >> 32)) << 32);  // < 2 d
         const uint64_t r2 = r - d;
         return (int64_t)r2 < 0 ? r : r2;  // d <= 2^63 and r < 2 d: r - d is "negative" exactly when r < d
     } else {
@@ -205,7 +208,7 @@ k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts
     ulonglong2* tab2 = tab + 8;                                      // 16 x 16 B: per-base-pair seed constants {fw, rc}
     uint64_t* sw = smem + 48;                                        // packed tile + halo
     uint32_t* stage = reinterpret_cast<uint32_t*>(sw + tile_words + (tile_words & 1));  // [nb][C], 16-byte aligned rows
-    // cnt[2][nb]: next free staging index of every bucket, ABSOLUTE (row b starts at b * C), for this / the next sub-step
+    // cnt[2][nb]: entries staged in every bucket's row, for this / the next sub-step
     uint32_t* cnt = stage + (size_t)nb * C;
     // capacity and entry array of every bucket, copied here once: the copy-out reads them for every row and sub-step,
     // and a global load there is latency nobody hides (ncu: the capacity test was the kernel's top stall line)
@@ -221,13 +224,12 @@ k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts
         const int c0 = tid & 3, c1 = tid >> 2;
         tab2[tid] = make_ulonglong2(rotl1(lemire_T(c0)) ^ lemire_T(c1), lemire_T(3 - c0) ^ rotl1(lemire_T(3 - c1)));
     }
-    for (int b = tid; b < 2 * nb; b += TILE_THREADS) cnt[b] = (uint32_t)(b < nb ? b : b - nb) * C;
+    for (int b = tid; b < 2 * nb; b += TILE_THREADS) cnt[b] = 0;
     for (int b = tid; b < nb; b += TILE_THREADS) {
         s_cap[b] = __ldg(bp.bcap + b);
         s_dst[b] = bp.bptr[b];
     }
     const uint64_t n_tiles = (a.n_bases + TILE_POS - 1) / TILE_POS;
-    const uint32_t slot_mask = (uint32_t)((1ull << bp.shift) - 1);
     unsigned long long direct = 0, dropped = 0;
     int phase = 0;  // which half of cnt[] the current sub-step appends to
     const uint32_t R = bp.piece, C4 = (C + 3u) & ~3u;
@@ -299,16 +301,37 @@ k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts
             }
             rok = !(__ldg(a.flags + r) & READ_INVALID);
         }
+        // vmask bit i: position p0 + i starts a k-mer that lies inside one valid read (dbg.hh:296-305 walks every read
+        // on its own; here the reads are back to back in one stream).  Worked out once per thread from the read
+        // boundaries, so that the 32 steps below test a bit instead of comparing 64-bit positions.
+        uint32_t vmask = 0;
+        if (live) {
+            const uint32_t n_here = (uint32_t)min((uint64_t)POS_PER_THREAD, a.n_bases - p0);
+            uint32_t i = 0;
+            while (true) {
+                const uint64_t left = rend - (p0 + i);                 // positions of read r from p0 + i on (>= 0)
+                const uint32_t seg_end = left < (uint64_t)(n_here - i) ? i + (uint32_t)left : n_here;  // read r covers [i, seg_end)
+                if (rok && left >= (uint64_t)K) {
+                    const uint64_t starts = left - (uint64_t)K + 1;   // valid k-mer starts from i on
+                    const uint32_t hi = starts < (uint64_t)(n_here - i) ? i + (uint32_t)starts : n_here;  // bits [i, hi)
+                    if (hi > i) vmask |= (hi - i >= 32u ? 0xFFFFFFFFu : ((1u << (hi - i)) - 1u)) << i;
+                }
+                i = seg_end;
+                if (i >= n_here) break;
+                ++r;
+                rend = __ldg(a.offsets + r + 1) - a.base0;
+                rok = !(__ldg(a.flags + r) & READ_INVALID);
+            }
+        }
 
         for (int sub = 0; sub < POS_PER_THREAD / BK_SUB; ++sub) {
             uint32_t* cn = cnt + phase * nb;
             // ---- append: roll, reduce, stage ------------------------------------------------------
-            if (live) {
+            if (vmask >> (sub * BK_SUB)) {  // a k-mer starts here or later in this thread's run (else the hashes are not needed any more)
+                const uint32_t slot_mask = bp.slot_mask;
 #pragma unroll 4
                 for (int ii = 0; ii < BK_SUB; ++ii) {
                     const int i = sub * BK_SUB + ii;
-                    const uint64_t p = p0 + i;
-                    if (p >= a.n_bases) break;
                     if (i) {
                         int out = (int)((wo >> (2 * (i - 1))) & 3);
                         int in = (int)((win >> (2 * i)) & 3);
@@ -316,23 +339,15 @@ k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts
                         fw = rotl1(fw) ^ to.x ^ ti.x;
                         if (CAN) rc = rotr1(rc ^ ti.y ^ to.y);
                     }
-                    if (p >= rend) {
-                        do {
-                            ++r;
-                            rend = __ldg(a.offsets + r + 1) - a.base0;
-                        } while (p >= rend);
-                        rok = !(__ldg(a.flags + r) & READ_INVALID);
-                    }
-                    if (rok && p + (uint64_t)K <= rend) {
+                    if ((vmask >> i) & 1u) {
                         const uint64_t h = CAN ? (fw < rc ? fw : rc) : fw;  // Canonical::value(), canonical.hh:124-126
                         uint32_t full = 0;  // tables whose row was full (skewed input): handled behind the loop, off the hot path
 #pragma unroll
                         for (int t = 0; t < nt; ++t) {
                             const uint64_t bin = bin_of_t<BIG>(h, ts, bp, t);
                             const uint32_t b = bp.first[t] + (uint32_t)(bin >> bp.shift);
-                            const uint32_t off = (uint32_t)bin & slot_mask;
-                            const uint32_t idx = atomicAdd(&cn[b], 1u);  // absolute staging index
-                            if (idx < b * C + C) stage[idx] = off;
+                            const uint32_t idx = atomicAdd(&cn[b], 1u);
+                            if (idx < C) stage[b * C + idx] = (uint32_t)bin & slot_mask;
                             else full |= 1u << t;
                         }
                         if (full) {
@@ -359,8 +374,8 @@ k_bucket(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts
                 const int mine = warp + rr * TILE_THREADS + 8 * lane;  // TILE_THREADS / 32 == 8 warps
                 if (mine >= nb) break;
                 const uint32_t row0 = (uint32_t)mine * C;
-                const uint32_t n = min(cn[mine] - row0, C);
-                cz[mine] = row0;  // the other half is idle now: rewind it for the next sub-step
+                const uint32_t n = min(cn[mine], C);
+                cz[mine] = 0;  // the other half is idle now: rewind it for the next sub-step
                 if (n == 0) continue;
                 const uint32_t n4 = (n + 3u) & ~3u;
                 uint32_t* row = stage + row0;

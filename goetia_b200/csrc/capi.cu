@@ -2233,6 +2233,7 @@ extern "C" int64_t gt_insert_and_query_sequences(gt_storage* st, int shifter, in
         a.counts = sl.out16.as<int16_t>();
         a.done = d_done;
         a.n_left = d_left;
+        a.n_unique = st->d_n_unique;
         const uint64_t n_tiles = (view.n_bases + TILE_POS - 1) / TILE_POS;
         const uint64_t per = std::max<uint64_t>(1, ((1ull << exact_log2_cap()) / 2) / ((uint64_t)TILE_POS * st->n));
         if (direct_begin(st, s)) return -1;

@@ -263,10 +263,11 @@ __device__ __forceinline__ bool storage_holds_all(const TableSet& ts, const Clai
 }
 // Storage::insert_and_query of a k-mer that holds all its slots this round: the count after its own insert
 template <int KIND, int NT>
-__device__ __forceinline__ uint32_t storage_insert_and_query(const TableSet& ts, uint64_t h) {
+__device__ __forceinline__ uint32_t storage_insert_and_query(const TableSet& ts, uint64_t h, bool& is_new) {
     const int nt = NT > 0 ? NT : ts.n;
     constexpr uint32_t fmax = KIND == 0 ? 1u : KIND == 1 ? 255u : 15u;
     uint32_t acc = fmax;
+    is_new = false;  // Storage::insert's return value: some table's slot was empty (counts towards n_unique)
 #pragma unroll
     for (int i = 0; i < nt; ++i) {
         const uint64_t bin = fastmod_u64(h, ts.size[i], ts.magic[i]);
@@ -278,9 +279,13 @@ __device__ __forceinline__ uint32_t storage_insert_and_query(const TableSet& ts,
             const uint32_t b = __ldcg(reinterpret_cast<const uint8_t*>(ts.ptr[i]) + (bin >> 1));
             v = (bin & 1) ? (b & 15u) : (b >> 4);
         }
-        if constexpr (KIND != 0) v = min(fmax, v + 1u);
+        if constexpr (KIND != 0) {
+            is_new |= v == 0u;
+            v = min(fmax, v + 1u);
+        }
         acc = min(acc, v);
-        slot_insert<KIND, false>(ts.ptr[i], bin);
+        const bool was_empty = slot_insert<KIND, KIND == 0>(ts.ptr[i], bin);
+        if constexpr (KIND == 0) is_new |= was_empty;
     }
     return acc;
 }
@@ -540,7 +545,7 @@ k_walk(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts) 
     }
     uint64_t n_tiles = (a.n_bases + TILE_POS - 1) / TILE_POS;
     if (a.tile_n && a.tile_lo + a.tile_n < n_tiles) n_tiles = a.tile_lo + a.tile_n;
-    unsigned long long block_new = 0;
+    unsigned long long block_new = 0, iq_new = 0;
     constexpr bool COUNT_NEW = (OP == OP_INSERT && TRACK) || OP == OP_INSERT_EXACT;
     constexpr bool COUNT_LEFT = OP == OP_IQ_APPLY;
 
@@ -640,8 +645,10 @@ k_walk(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts) 
                     } else if constexpr (OP == OP_IQ_APPLY) {
                         if (!a.done[p]) {
                             if (storage_holds_all<KIND, NT>(ts, a.claims, h, (uint32_t)p)) {
-                                a.counts[a.koff[r] + (p - rstart)] = (int16_t)storage_insert_and_query<KIND, NT>(ts, h);
+                                bool nw;
+                                a.counts[a.koff[r] + (p - rstart)] = (int16_t)storage_insert_and_query<KIND, NT>(ts, h, nw);
                                 a.done[p] = 1;
+                                iq_new += nw;
                             } else {
                                 ++block_new;  // left for the next round
                             }
@@ -673,6 +680,10 @@ k_walk(const __grid_constant__ WalkArgs a, const __grid_constant__ TableSet ts) 
     if constexpr (COUNT_NEW || COUNT_LEFT) {
         for (int o = 16; o; o >>= 1) block_new += __shfl_down_sync(0xffffffffu, block_new, o);
         if ((tid & 31) == 0 && block_new) atomicAdd(COUNT_LEFT ? a.n_left : a.n_unique, block_new);
+    }
+    if constexpr (OP == OP_IQ_APPLY) {  // k-mers that were new to the storage count towards n_unique, as Storage::insert does
+        for (int o = 16; o; o >>= 1) iq_new += __shfl_down_sync(0xffffffffu, iq_new, o);
+        if ((tid & 31) == 0 && iq_new && a.n_unique) atomicAdd(a.n_unique, iq_new);
     }
 }
 
