@@ -13,7 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "capi.cu")
-DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("kernels.cuh", "sketch.cuh", "sketch_host.inc", "bucket.cuh",
+SRC_HOST = os.path.join(HERE, "csrc", "pack_simd.cpp")  # host-only helpers (AVX2 where the CPU has it)
+DEPS = [SRC, SRC_HOST] + [os.path.join(HERE, "csrc", f) for f in ("kernels.cuh", "sketch.cuh", "sketch_host.inc", "bucket.cuh",
                                                           "bucket_host.inc", "fastx_host.inc")] + [os.path.join(ROOT, "include", "goetia_b200.h")]
 OUT = os.path.join(HERE, "libgoetia_b200.so")
 
@@ -44,7 +45,7 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC] + LIBS
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC, SRC_HOST] + LIBS
     if verbose:
         print(" ".join(cmd))
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -1018,53 +1018,20 @@ static int insert_sequences_dev_queue(gt_storage* st, int shifter, int K, const 
 // folded to upper case; a read holding any other byte gets flags[r] = GT_READ_INVALID (DNA_SIMPLE validation,
 // sequences/alphabets.hh:112-130, parsing/readers.hh:162-171) and its codes are unspecified.
 // ------------------------------------------------------------------------------------------
-static inline uint32_t host_pack8(uint64_t x, bool& bad) {
-    // per byte: code = ((c>>1)&3) ^ ((c>>2)&1); validity: (c & 0xDF) in {A, C, G, T}  (same arithmetic as k_pack)
-    uint64_t code = ((x >> 1) & 0x0303030303030303ull) ^ ((x >> 2) & 0x0101010101010101ull);
-    const uint64_t u = x & 0xDFDFDFDFDFDFDFDFull, L = 0x7F7F7F7F7F7F7F7Full;
-    uint64_t ok = 0;
-    for (uint64_t pat : {0x41ull, 0x43ull, 0x47ull, 0x54ull}) {
-        const uint64_t t = u ^ (pat * 0x0101010101010101ull);
-        ok |= ~(((t & L) + L) | t | L);
-    }
-    bad |= ok != 0x8080808080808080ull;
-    code = (code | (code >> 6)) & 0x000F000F000F000Full;
-    code = (code | (code >> 12)) & 0x000000FF000000FFull;
-    code = (code | (code >> 24)) & 0xFFFFull;
-    return (uint32_t)code;
-}
+extern "C" int gt_host_pack_append(const unsigned char* s, size_t L, uint64_t* words, uint64_t pos);  // pack_simd.cpp (AVX2 / portable)
 
 static void host_pack_range(const char* bases, const uint64_t* offsets, uint64_t n_reads, uint64_t base0, uint64_t w_lo, uint64_t w_hi,
                             uint64_t n_bases, uint64_t* words, uint8_t* flags) {
-    for (uint64_t w = w_lo; w < w_hi; ++w) {
-        const uint64_t p = w * 32;
-        uint64_t out = 0;
-        bool bad = false;
-        if (p + 32 <= n_bases) {
-            for (int k = 0; k < 4; ++k) {
-                uint64_t x;
-                memcpy(&x, bases + base0 + p + 8 * k, 8);
-                out |= (uint64_t)host_pack8(x, bad) << (16 * k);
-            }
-        } else {
-            for (int k = 0; k < 4; ++k) {
-                uint64_t x = 0;
-                for (int j = 0; j < 8; ++j) {
-                    const uint64_t q = p + 8 * k + j;
-                    x |= (uint64_t)(q < n_bases ? (unsigned char)bases[base0 + q] : (unsigned char)'A') << (8 * j);
-                }
-                out |= (uint64_t)host_pack8(x, bad) << (16 * k);
-            }
-        }
-        words[w] = out;
-        if (bad) {  // rare: flag every read owning an offending byte
-            for (uint64_t q = p; q < std::min(p + 32, n_bases); ++q) {
-                const unsigned char c = (unsigned char)bases[base0 + q] & 0xDF;
-                if (c != 'A' && c != 'C' && c != 'G' && c != 'T') {
-                    const uint64_t r = (uint64_t)(std::upper_bound(offsets, offsets + n_reads + 1, base0 + q) - offsets) - 1;
-                    __atomic_store_n(flags + r, (uint8_t)GT_READ_INVALID, __ATOMIC_RELAXED);
-                }
-            }
+    if (w_lo >= w_hi) return;
+    const uint64_t p_lo = w_lo * 32, p_hi = std::min(w_hi * 32, n_bases);
+    memset(words + w_lo, 0, (w_hi - w_lo) * 8);
+    // word-aligned ranges: nothing is written outside [w_lo, w_hi)
+    if (!gt_host_pack_append(reinterpret_cast<const unsigned char*>(bases) + base0 + p_lo, p_hi - p_lo, words, p_lo)) return;
+    for (uint64_t q = p_lo; q < p_hi; ++q) {  // rare: flag every read owning an offending byte
+        const unsigned char c = (unsigned char)bases[base0 + q] & 0xDF;
+        if (c != 'A' && c != 'C' && c != 'G' && c != 'T') {
+            const uint64_t r = (uint64_t)(std::upper_bound(offsets, offsets + n_reads + 1, base0 + q) - offsets) - 1;
+            __atomic_store_n(flags + r, (uint8_t)GT_READ_INVALID, __ATOMIC_RELAXED);
         }
     }
 }

@@ -102,6 +102,22 @@ class FastxParser:
             self._raise(n)
         return bases[:int(offsets[n])], offsets[:n + 1]
 
+    def next_packed_batch(self, max_bases=64 << 20, max_reads=None):
+        """The next kept records 2-bit packed, as gt_insert_sequences_packed / dBG.insert_sequences_packed take them:
+        (words uint64, offsets uint64, flags uint8, n_records).  Entries flagged READ_INVALID are alignment gaps between the
+        pieces the parser's workers packed, not records; offsets.size == 1 at the end of the file."""
+        L = _capi.load()
+        max_reads = int(max_reads) if max_reads else max(1024, max_bases // 32)
+        words = np.zeros(max_bases // 32 + 2, dtype=np.uint64)
+        offsets = np.zeros(max_reads + 1, dtype=np.uint64)
+        flags = np.zeros(max_reads, dtype=np.uint8)
+        n_real = C.c_uint64(0)
+        n = L.gt_fastx_next_packed_batch(self._h, words.ctypes.data, words.size, offsets.ctypes.data, flags.ctypes.data, max_reads,
+                                         C.byref(n_real))
+        if n < 0:
+            self._raise(n)
+        return words[:(int(offsets[n]) + 31) // 32], offsets[:n + 1], flags[:n], int(n_real.value)
+
     def _stats(self):
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_int()
         _capi.check(_capi.load().gt_fastx_stats(self._h, C.byref(a), C.byref(b), C.byref(c)), "gt_fastx_stats")

@@ -386,6 +386,14 @@ int gt_fastx_next_record(gt_fastx* fx, const char** name, uint64_t* name_len, co
  * Returns n (0 = end of file), or an error code as above. */
 int64_t gt_fastx_next_batch(gt_fastx* fx, char* bases, uint64_t max_bases, uint64_t* offsets,
                             uint64_t max_reads);
+/* The same in the device pipeline's own transfer format: the sequences 2-bit packed (base p of the batch at bits
+ * 2*(p%32) of word p/32, A=0 C=1 G=2 T=3) -- what gt_insert_sequences_packed takes.  For uncompressed files the
+ * parser's worker threads pack while they parse and whole verified pieces are handed out; every piece starts on a
+ * word boundary and the gap behind it is covered by a phantom read flagged GT_READ_INVALID, so the return value n
+ * (entries of offsets[1..n] and flags[0..n)) can exceed *n_real, the number of records.  words: at least
+ * max_words (>= 2) u64; offsets: max_reads + 1; flags: max_reads.  0 = end of file, < 0 = error as above. */
+int64_t gt_fastx_next_packed_batch(gt_fastx* fx, uint64_t* words, uint64_t max_words, uint64_t* offsets,
+                                   uint8_t* flags, uint64_t max_reads, uint64_t* n_real);
 /* n_parsed(), n_skipped(), is_complete() (readers.hh:205-215). */
 int gt_fastx_stats(const gt_fastx* fx, uint64_t* n_parsed, uint64_t* n_skipped, int* is_complete);
 /* FileProcessor<InserterProcessor<dBG>>::process / advance (processors.hh:112-127, 208-229, 304-331):

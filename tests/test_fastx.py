@@ -86,6 +86,61 @@ def test_parser_matches_reference(tmp_path, case, gz, engine):
         assert seqs3 == seqs and stats3 == stats
 
 
+def unpack_batch(words, offsets, flags):
+    """The records of a packed batch as text (entries flagged READ_INVALID are alignment gaps, not records)."""
+    n = int(offsets[-1])
+    codes = ((np.repeat(words, 32)[:n] >> (2 * (np.arange(n, dtype=np.uint64) % np.uint64(32)))) & np.uint64(3)).astype(np.uint8)
+    text = np.frombuffer(b"ACGT", dtype=np.uint8)[codes]
+    return [text[int(offsets[i]):int(offsets[i + 1])].tobytes() for i in range(offsets.size - 1) if not flags[i]]
+
+
+@pytest.mark.parametrize("gz", [False, True])
+@pytest.mark.parametrize("case", [c for c in cases()], ids=lambda c: c[0])
+def test_packed_batches_match_reference(tmp_path, case, gz, engine):
+    """gt_fastx_next_packed_batch (what gt_insert_fastx feeds the device with): unpacked again, the records are the
+    reference parser's.  Kept records hold ACGT only (after case folding), so the 2-bit form loses nothing."""
+    from goetia_b200 import parsing
+    name, data, min_length, strict = case
+    fn = write_case(str(tmp_path), name, data, gz)
+    want = GOLD[os.path.basename(fn)]
+    p = parsing.FastxParser(fn, strict, min_length)
+    seqs, n_real = [], 0
+    try:
+        while True:
+            w, o, f, nr = p.next_packed_batch(8 << 20)
+            if o.size == 1:
+                break
+            got = unpack_batch(w, o, f)
+            assert len(got) == nr
+            seqs.extend(got)
+            n_real += nr
+        assert "error" not in want
+    except (parsing.InvalidRead, parsing.InvalidCharacterException):
+        assert "error" in want
+        return
+    finally:
+        stats = (p.n_parsed(), p.n_skipped(), p.is_complete())
+        p.close()
+    check(seqs, stats, want)
+
+
+def test_host_pack_scalar_equals_avx2(tmp_path):
+    """The portable packer and the AVX2 one give the same words (the choice is made once per process, so the scalar
+    run is a second process)."""
+    import subprocess
+    import sys
+    name, data, min_length, strict = [c for c in cases() if c[0] == "reads.fq"][0]
+    fn = write_case(str(tmp_path), name, data, False)
+    prog = ("import sys; sys.path.insert(0, %r); import numpy as np; from goetia_b200.parsing import FastxParser; "
+            "from oracle.binding import Port; p = FastxParser(%r); w, o, f, n = p.next_packed_batch(1 << 20); "
+            "print(n, Port.fnv1a(w.view(np.uint8)), Port.fnv1a(o.view(np.uint8)))" % (ROOT, fn))
+    outs = []
+    for scalar in ("0", "1"):
+        env = dict(os.environ, GT_HOST_PACK_SCALAR=scalar, GT_FASTX_THREADS="1")
+        outs.append(subprocess.check_output([sys.executable, "-c", prog], env=env).decode().split())
+    assert outs[0] == outs[1] and int(outs[0][0]) == GOLD["reads.fq"]["n_reads"]
+
+
 def test_records_and_errors(tmp_path, golden):
     from goetia_b200 import parsing
     for key in ("_mixed.fa", "_mixed.fq"):
