@@ -24,6 +24,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "kernels.cuh"
 
 namespace gt {
@@ -863,19 +865,25 @@ k_rebucket2(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ i
     if (cur_slice >= 0) flush(true);
 }
 
-template <int KIND>
+// EXACT: the saturating increment as a compare-and-swap loop.  !EXACT (counting storages): a plain add of 1 << field --
+// right as long as no field of the image receives more hits than it can hold (checked afterwards, see k_apply_win).
+template <int KIND, bool EXACT>
 __device__ __forceinline__ void window_update(uint32_t* __restrict__ win, uint32_t off) {
     if constexpr (KIND == 0) {
         atomicOr(win + (off >> 5), 1u << (off & 31));
     } else {
         uint32_t word, sh;
         counter_addr<KIND>(off, word, sh);
-        constexpr uint32_t fmax = KIND == 1 ? 255u : 15u;
-        uint32_t old = win[word];
-        while (((old >> sh) & fmax) != fmax) {
-            const uint32_t prev = atomicCAS(win + word, old, old + (1u << sh));
-            if (prev == old) break;
-            old = prev;
+        if constexpr (!EXACT) {
+            atomicAdd(win + word, 1u << sh);
+        } else {
+            constexpr uint32_t fmax = KIND == 1 ? 255u : 15u;
+            uint32_t old = win[word];
+            while (((old >> sh) & fmax) != fmax) {
+                const uint32_t prev = atomicCAS(win + word, old, old + (1u << sh));
+                if (prev == old) break;
+                old = prev;
+            }
         }
     }
 }
@@ -891,13 +899,29 @@ __device__ __forceinline__ uint32_t window_merge(uint32_t t, uint32_t d) {
     }
 }
 
+// sum of the counters held in one image word
+template <int KIND>
+__device__ __forceinline__ uint32_t field_sum(uint32_t w) {
+    if constexpr (KIND == 1) return __dp4a(w, 0x01010101u, 0u);
+    else return __dp4a(w & 0x0f0f0f0fu, 0x01010101u, __dp4a((w >> 4) & 0x0f0f0f0fu, 0x01010101u, 0u));
+}
+
 // One CTA per window.  TWO_LEVEL: the window's sub-bucket (k_rebucket's output); otherwise the slice is the window
 // and its sources are the level-1 items [slice * items_per_slice, +items_per_slice).
+//
+// Counting storages: the image is first built OPTIMISTICALLY with plain shared-memory adds of 1 << field (as cheap as
+// the Bloom filter's OR; the CAS loop costs three times as much).  Every add raises the sum of the image's fields by
+// exactly one unless it finds its field at the maximum -- then the field wraps to 0 and carries into its neighbour,
+// and the sum drops by at least max - 1.  So "sum of all fields == entries applied" holds exactly when no field was
+// asked to hold more than it can (a counter hit more than 255 / 15 times by ONE apply: poly-A input); the CTA checks
+// it before the merge and otherwise rebuilds the image with the saturating CAS.  Either way the image holds
+// min(max, hits) and the merge adds it to the table with per-field saturation.
 template <int KIND, bool TWO_LEVEL>
 __global__ void __launch_bounds__(AW_THREADS)
 k_apply_win(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ items, int items_per_slice,
             const SliceWin* __restrict__ slices, const uint32_t* __restrict__ win_slice, int wshift) {
     extern __shared__ __align__(16) uint32_t win[];
+    __shared__ uint32_t s_red[2 * (AW_THREADS / 32)];
     const uint32_t s = __ldg(win_slice + blockIdx.x);
     const SliceWin sl = slices[s];
     const uint32_t d = blockIdx.x - sl.win0;
@@ -919,61 +943,71 @@ k_apply_win(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ i
     if (total == 0) return;  // nothing for this window: the table is not touched
     const int tid = threadIdx.x;
     uint4* win4 = reinterpret_cast<uint4*>(win);
-    for (uint32_t i = tid; i < nwords / 4; i += AW_THREADS) win4[i] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
-    for (int q = 0; q < n_src; ++q) {
-        const uint32_t* src;
-        uint32_t n;
-        if constexpr (TWO_LEVEL) {
-            src = sl.sub + (size_t)d * sl.cap2;
-            n = total;
-        } else {
-            const ApplyItem it = items[s * (uint32_t)items_per_slice + q];
-            src = it.src;
-            n = min(__ldcg(it.fill), it.cap);
+
+    // zero the image, then stream the entries into it; returns the entries this thread applied (pads excluded)
+    auto build = [&](auto exact_tag) -> uint32_t {
+        constexpr bool EXACT = decltype(exact_tag)::value;
+        uint32_t applied = 0;
+        for (uint32_t i = tid; i < nwords / 4; i += AW_THREADS) win4[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        auto one = [&](uint32_t x) {
+            if (x != BK_PAD) {
+                window_update<KIND, EXACT>(win, x);
+                if constexpr (KIND != 0 && !EXACT) ++applied;
+            }
+        };
+        auto four = [&](const uint4& v) { one(v.x); one(v.y); one(v.z); one(v.w); };
+        for (int q = 0; q < n_src; ++q) {
+            const uint32_t* src;
+            uint32_t n;
+            if constexpr (TWO_LEVEL) {
+                src = sl.sub + (size_t)d * sl.cap2;
+                n = total;
+            } else {
+                const ApplyItem it = items[s * (uint32_t)items_per_slice + q];
+                src = it.src;
+                n = min(__ldcg(it.fill), it.cap);
+            }
+            // 16 B streaming loads over the aligned body, scalar head / tail
+            const uint32_t head = min(n, (uint32_t)((16 - (reinterpret_cast<uintptr_t>(src) & 15)) & 15) / 4);
+            if ((uint32_t)tid < head) one(__ldcs(src + tid));
+            const uint32_t body = (n - head) / 4;
+            const uint4* v = reinterpret_cast<const uint4*>(src + head);
+            uint32_t i = tid;
+            for (; i + 3 * AW_THREADS < body; i += 4 * AW_THREADS) {
+                const uint4 a = __ldcs(v + i), b = __ldcs(v + i + AW_THREADS), c = __ldcs(v + i + 2 * AW_THREADS), e = __ldcs(v + i + 3 * AW_THREADS);
+                four(a); four(b); four(c); four(e);
+            }
+            for (; i < body; i += AW_THREADS) four(__ldcs(v + i));
+            const uint32_t tail0 = head + body * 4;
+            if (tail0 + tid < n) one(__ldcs(src + tail0 + tid));
         }
-        // 16 B streaming loads over the aligned body, scalar head / tail
-        const uint32_t head = min(n, (uint32_t)((16 - (reinterpret_cast<uintptr_t>(src) & 15)) & 15) / 4);
-        if ((uint32_t)tid < head) {
-            const uint32_t x = __ldcs(src + tid);
-            if (x != BK_PAD) window_update<KIND>(win, x);
+        __syncthreads();
+        return applied;
+    };
+
+    if constexpr (KIND == 0) {
+        build(std::true_type{});
+    } else {
+        uint32_t applied = build(std::false_type{});
+        uint32_t sum = 0;
+        for (uint32_t i = tid; i < nwords / 4; i += AW_THREADS) {
+            const uint4 w = win4[i];
+            sum += field_sum<KIND>(w.x) + field_sum<KIND>(w.y) + field_sum<KIND>(w.z) + field_sum<KIND>(w.w);
         }
-        const uint32_t body = (n - head) / 4;
-        const uint4* v = reinterpret_cast<const uint4*>(src + head);
-        uint32_t i = tid;
-        for (; i + 3 * AW_THREADS < body; i += 4 * AW_THREADS) {
-            const uint4 a = __ldcs(v + i), b = __ldcs(v + i + AW_THREADS), c = __ldcs(v + i + 2 * AW_THREADS), e = __ldcs(v + i + 3 * AW_THREADS);
-            if (a.x != BK_PAD) window_update<KIND>(win, a.x);
-            if (a.y != BK_PAD) window_update<KIND>(win, a.y);
-            if (a.z != BK_PAD) window_update<KIND>(win, a.z);
-            if (a.w != BK_PAD) window_update<KIND>(win, a.w);
-            if (b.x != BK_PAD) window_update<KIND>(win, b.x);
-            if (b.y != BK_PAD) window_update<KIND>(win, b.y);
-            if (b.z != BK_PAD) window_update<KIND>(win, b.z);
-            if (b.w != BK_PAD) window_update<KIND>(win, b.w);
-            if (c.x != BK_PAD) window_update<KIND>(win, c.x);
-            if (c.y != BK_PAD) window_update<KIND>(win, c.y);
-            if (c.z != BK_PAD) window_update<KIND>(win, c.z);
-            if (c.w != BK_PAD) window_update<KIND>(win, c.w);
-            if (e.x != BK_PAD) window_update<KIND>(win, e.x);
-            if (e.y != BK_PAD) window_update<KIND>(win, e.y);
-            if (e.z != BK_PAD) window_update<KIND>(win, e.z);
-            if (e.w != BK_PAD) window_update<KIND>(win, e.w);
+        for (int o = 16; o; o >>= 1) {
+            applied += __shfl_down_sync(0xffffffffu, applied, o);
+            sum += __shfl_down_sync(0xffffffffu, sum, o);
         }
-        for (; i < body; i += AW_THREADS) {
-            const uint4 a = __ldcs(v + i);
-            if (a.x != BK_PAD) window_update<KIND>(win, a.x);
-            if (a.y != BK_PAD) window_update<KIND>(win, a.y);
-            if (a.z != BK_PAD) window_update<KIND>(win, a.z);
-            if (a.w != BK_PAD) window_update<KIND>(win, a.w);
-        }
-        const uint32_t tail0 = head + body * 4;
-        if (tail0 + tid < n) {
-            const uint32_t x = __ldcs(src + tail0 + tid);
-            if (x != BK_PAD) window_update<KIND>(win, x);
+        if ((tid & 31) == 0) { s_red[tid >> 5] = applied; s_red[AW_THREADS / 32 + (tid >> 5)] = sum; }
+        __syncthreads();
+        uint32_t a_all = 0, s_all = 0;
+        for (int w = 0; w < AW_THREADS / 32; ++w) { a_all += s_red[w]; s_all += s_red[AW_THREADS / 32 + w]; }
+        if (a_all != s_all) {  // some counter was hit more often than it can count: saturate properly
+            __syncthreads();
+            build(std::true_type{});
         }
     }
-    __syncthreads();
     // merge the image into the table: one coalesced read-modify-write of the window
     uint4* tbl4 = reinterpret_cast<uint4*>(slice_words_ptr<KIND>(ts, sl.table, sl.slot0) + w_lo);
     for (uint32_t i = tid; i < nwords / 4; i += AW_THREADS) {

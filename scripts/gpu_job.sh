@@ -1,5 +1,6 @@
 set -x
-timeout 900 python -m pytest tests/test_fastx.py tests/test_packed.py tests/test_gpu_processors.py -x -q -m gpu > gpurun_out/j_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/j_pytest.log
-timeout 900 python scripts/bench_fastx.py --reads 16000000 --out gpurun_out/j_fastx2.json > gpurun_out/j_fastx2.log 2>&1; echo "rc=$?"
-GT_FASTX_THREADS=16 timeout 900 python scripts/bench_fastx.py --reads 16000000 --out gpurun_out/j_fastx2_t16.json > gpurun_out/j_fastx2_t16.log 2>&1; echo "rc=$?"
-GT_FASTX_THREADS=12 timeout 900 python scripts/bench_fastx.py --reads 16000000 --out gpurun_out/j_fastx2_t12.json > gpurun_out/j_fastx2_t12.log 2>&1; echo "rc=$?"
+timeout 900 python -m pytest tests/test_gpu_bucket.py tests/test_gpu_fullsize.py -x -q -m gpu > gpurun_out/j_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/j_pytest.log
+B="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e"
+timeout 300 $B --workload c2 > gpurun_out/j_c2.json 2> gpurun_out/j_err3.err; echo "rc=$?"
+timeout 300 $B --workload c5 > gpurun_out/j_c5.json 2> gpurun_out/j_err4.err; echo "rc=$?"
+GT_BUCKET_OVERLAP=0 timeout 300 $B --workload c2 > gpurun_out/j_c2_noovl.json 2> gpurun_out/j_err5.err; echo "rc=$?"
