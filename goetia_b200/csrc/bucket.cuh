@@ -522,9 +522,8 @@ __device__ __forceinline__ void counter_addr(uint32_t off, uint32_t& word, uint3
 // storages a saturating increment needs a CAS (load + compare-and-swap, ~26 G/s).  Shared-memory atomics are an
 // order of magnitude cheaper, so a slice is cut once more into WINDOWS of 2^wshift slots that fit shared memory:
 //
-//   k_rebucket   radix-partitions the entries of a slice (all sources) by window: per 8192-entry chunk a counting
-//                sort in shared memory, one global cursor reservation per (chunk, window), runs written out
-//                coalesced to the window's SUB-BUCKET (entries become window-local offsets);
+//   k_rebucket2  partitions the entries of a slice (all sources) by window through per-window staging rows in shared
+//                memory (below): runs of window-local offsets appended to the window's SUB-BUCKET;
 //   k_apply_win  one CTA per window: zero the window image in shared memory, stream the sub-bucket with 16 B loads
 //                and OR / saturating-add into shared memory, then merge the image into the table ONCE with 16 B
 //                loads and stores (table |= image; per-byte / per-nibble saturating add for the counting storages).
@@ -532,15 +531,13 @@ __device__ __forceinline__ void counter_addr(uint32_t off, uint32_t& word, uint3
 // The image of a counting window holds the hits of this apply per counter, saturating at the counter's maximum, so
 // table' = min(max, table + min(max, hits)) = min(max, table + hits): exactly the reference's one-at-a-time
 // saturating increments (bytestorage.cc:60-113, nibblestorage.cc:60-100) in any order.  Slices that are not larger
-// than a window skip k_rebucket (n_win == 1: the level-1 entries already are window-local).
+// than a window skip k_rebucket2 (n_win == 1: the level-1 entries already are window-local).
 // The merge is a plain read-modify-write, so nothing else may write the tables while an apply runs: k_bucket
 // parks the updates that overflow a bucket of its own slots in the store's spill list (ProducePlan::own_spill,
 // applied after the store's windows), a sub-bucket that overflows applies the excess with global atomics from
-// k_rebucket (which runs before any window of that apply), and the direct writers (k_walk, k_insert_hashes) are
+// k_rebucket2 (which runs before any window of that apply), and the direct writers (k_walk, k_insert_hashes) are
 // ordered against the apply stream (direct_begin / direct_end).
 // ------------------------------------------------------------------------------------------
-constexpr int RB_THREADS = 1024;
-constexpr int RB_PER_THREAD = AP_CHUNK / RB_THREADS;  // 8
 constexpr int AW_THREADS = 512;
 constexpr int WIN_MAX_PER_SLICE = 1024;
 
@@ -560,124 +557,13 @@ __device__ __forceinline__ uint32_t* slice_words_ptr(const TableSet& ts, uint32_
     return ts.ptr[table] + (KIND == 0 ? (slot0 >> 5) : KIND == 1 ? (slot0 >> 2) : (slot0 >> 3));
 }
 
-__device__ __forceinline__ uint32_t item_of_chunk(const uint32_t* __restrict__ chunk_start, int n_items, uint32_t* s_b) {
-    if (threadIdx.x == 0) {
-        uint32_t lo = 0, hi = (uint32_t)n_items;
-        while (hi - lo > 1) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (__ldg(chunk_start + mid) <= blockIdx.x) lo = mid; else hi = mid;
-        }
-        *s_b = lo;
-    }
-    __syncthreads();
-    return *s_b;
-}
-
-// shared memory: sorted[AP_CHUNK] | hist[nw_max + 1] | lbase[nw_max + 1] | gbase[nw_max + 1]
-// One CTA = one 8192-entry chunk of one level-1 item; thread t holds 8 entries in registers.  Pad entries count
-// as window `nw` (one extra histogram bin, sorted to the end and never written out), so the per-entry code has no
-// branches.  The overflow check is per (chunk, window) at reservation time; the per-entry check runs only in a
-// chunk that hit a full sub-bucket.
-template <int KIND>
-__global__ void __launch_bounds__(RB_THREADS, 2)
-k_rebucket(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ items, const uint32_t* __restrict__ chunk_start,
-           int n_items, int items_per_slice, const SliceWin* __restrict__ slices, int wshift, int nw_max) {
-    extern __shared__ __align__(16) uint32_t rb_sm[];
-    __shared__ uint32_t s_b, s_ovf, wsum[RB_THREADS / 32];
-    const uint32_t b = item_of_chunk(chunk_start, n_items, &s_b);
-    const ApplyItem it = items[b];
-    const uint32_t fill = min(__ldcg(it.fill), it.cap);
-    const uint32_t e0 = (blockIdx.x - __ldg(chunk_start + b)) * (uint32_t)AP_CHUNK;
-    if (e0 >= fill) return;
-    const SliceWin sl = slices[b / (uint32_t)items_per_slice];
-    const uint32_t nw = sl.n_win;
-    uint32_t* sorted = rb_sm;
-    uint32_t* hist = rb_sm + AP_CHUNK;
-    uint32_t* lbase = hist + nw_max + 1;
-    uint32_t* gbase = lbase + nw_max + 1;
-    const int tid = threadIdx.x;
-    if ((uint32_t)tid < nw) hist[tid] = 0;
-    if (tid == 0) { hist[nw] = 0; s_ovf = 0; }
-    __syncthreads();
-    const uint32_t n = min((uint32_t)AP_CHUNK, fill - e0);
-    const uint32_t* src = it.src + e0;
-    uint32_t v[RB_PER_THREAD], r[RB_PER_THREAD];
-    if (n == AP_CHUNK && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-#pragma unroll
-        for (int k = 0; k < RB_PER_THREAD / 4; ++k) {
-            const uint4 x = __ldcs(reinterpret_cast<const uint4*>(src) + k * RB_THREADS + tid);
-            v[4 * k] = x.x; v[4 * k + 1] = x.y; v[4 * k + 2] = x.z; v[4 * k + 3] = x.w;
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < RB_PER_THREAD; ++k) {
-            const uint32_t e = (uint32_t)k * RB_THREADS + tid;
-            v[k] = e < n ? __ldcs(src + e) : BK_PAD;
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < RB_PER_THREAD; ++k) r[k] = atomicAdd(&hist[min(v[k] >> wshift, nw)], 1u);
-    __syncthreads();
-    // exclusive scan of hist[0 .. nw] (nw + 1 <= 1025 bins; bin nw = pads, handled by the last thread too)
-    const uint32_t h = (uint32_t)tid < nw ? hist[tid] : 0u;
-    uint32_t incl = h;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((tid & 31) >= o) incl += t;
-    }
-    if ((tid & 31) == 31) wsum[tid >> 5] = incl;
-    __syncthreads();
-    if (tid < 32) {
-        const uint32_t w = wsum[tid];
-        uint32_t wi = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
-            if (tid >= o) wi += t;
-        }
-        wsum[tid] = wi - w;  // exclusive
-    }
-    __syncthreads();
-    const uint32_t excl = wsum[tid >> 5] + incl - h;
-    if ((uint32_t)tid < nw) {
-        lbase[tid] = excl;
-        uint32_t g = 0;
-        if (h) {  // one reservation per (chunk, window) that received entries
-            g = atomicAdd(sl.sub_fill + tid, h);
-            if (g + h > sl.cap2) s_ovf = 1;
-        }
-        gbase[tid] = (uint32_t)tid * sl.cap2 + g - excl;
-    }
-    if (tid == RB_THREADS - 1) lbase[nw] = excl + h;  // == number of real entries (nw < RB_THREADS: h is 0 here unless nw == 1024)
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < RB_PER_THREAD; ++k) sorted[lbase[min(v[k] >> wshift, nw)] + r[k]] = v[k];
-    __syncthreads();
-    const uint32_t total = lbase[nw];
-    const uint32_t wmask = (1u << wshift) - 1u;
-    if (!s_ovf) {
-        for (uint32_t j = tid; j < total; j += RB_THREADS) {
-            const uint32_t x = sorted[j];
-            sl.sub[gbase[x >> wshift] + j] = x & wmask;
-        }
-    } else {  // some sub-bucket is full (skewed input): the excess is applied here; no window of this apply has started yet
-        for (uint32_t j = tid; j < total; j += RB_THREADS) {
-            const uint32_t x = sorted[j];
-            const uint32_t d = x >> wshift;
-            const uint32_t at = gbase[d] + j;
-            if (at - d * sl.cap2 < sl.cap2) sl.sub[at] = x & wmask;
-            else slot_insert<KIND, false>(ts.ptr[sl.table], sl.slot0 + x);
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------
-// k_rebucket2: the same partition by STAGING ROWS (as k_bucket does at level 1) instead of a counting sort.
+// k_rebucket2: the level-2 partition by STAGING ROWS (as k_bucket does at level 1).
 //
-// k_rebucket above is bound by shared-memory wavefronts and barriers (ncu, profiles/r2_ncu_full_v1.txt: 16
-// wavefronts per warp and entry -- histogram atomic, rank lookup, scatter, gather, base lookup -- and six barriers
-// per 8192 entries; 10.4 ms per 2.9 G entries against 3.7 ms for its 24 GB of DRAM traffic).  Here a persistent
+// (Its predecessor, a counting sort per 8192-entry chunk, was bound by shared-memory wavefronts and barriers -- ncu,
+// profiles/r2_ncu_full_v1.txt: 16 wavefronts per warp and entry for histogram atomic, rank lookup, scatter, gather and
+// base lookup, six barriers per chunk; 10.4 ms per 2.9 G entries against 3.7 ms for its 24 GB of DRAM traffic.)  A persistent
 // CTA keeps one row of C entries per window in shared memory; an entry costs ONE returning shared atomic (the
 // row cursor) and ONE shared store.  After every chunk (16 entries per thread) each row is sent to its sub-bucket by its owner
 // thread: one global cursor reservation and ONE bulk (TMA) copy shared -> global of the row's multiple-of-4
@@ -686,7 +572,7 @@ k_rebucket(const __grid_constant__ TableSet ts, const ApplyItem* __restrict__ it
 // 16 bytes and emptied).  The chunks of an item are dealt round-robin to the CTAs, item after item: all CTAs work
 // on the same slice at about the same time, so the slice's n_win output streams stay together in DRAM; the next
 // chunk is loaded into registers while the current one is staged.  A row that is full (skewed input) and a
-// sub-bucket that is full send the update straight to the table, as k_rebucket does.
+// sub-bucket that is full send the update straight to the table.
 // shared memory: cnt[nw_max + 1] (cnt[nw_max]: where pad entries count themselves) | stage[nw_max][C]
 // C/4 is odd: consecutive rows then start 4 banks apart modulo 32 (a multiple of 8 would put all rows on 2 or 4
 // bank groups: rows fill at the same pace, so the append positions of a warp would collide).
@@ -906,7 +792,7 @@ __device__ __forceinline__ uint32_t field_sum(uint32_t w) {
     else return __dp4a(w & 0x0f0f0f0fu, 0x01010101u, __dp4a((w >> 4) & 0x0f0f0f0fu, 0x01010101u, 0u));
 }
 
-// One CTA per window.  TWO_LEVEL: the window's sub-bucket (k_rebucket's output); otherwise the slice is the window
+// One CTA per window.  TWO_LEVEL: the window's sub-bucket (k_rebucket2's output); otherwise the slice is the window
 // and its sources are the level-1 items [slice * items_per_slice, +items_per_slice).
 //
 // Counting storages: the image is first built OPTIMISTICALLY with plain shared-memory adds of 1 << field (as cheap as

@@ -1,6 +1,11 @@
 set -x
-timeout 900 python -m pytest tests/test_gpu_bucket.py tests/test_gpu_fullsize.py -x -q -m gpu > gpurun_out/j_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/j_pytest.log
-B="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e"
-timeout 300 $B --workload c2 > gpurun_out/j_c2.json 2> gpurun_out/j_err3.err; echo "rc=$?"
-timeout 300 $B --workload c5 > gpurun_out/j_c5.json 2> gpurun_out/j_err4.err; echo "rc=$?"
-GT_BUCKET_OVERLAP=0 timeout 300 $B --workload c2 > gpurun_out/j_c2_noovl.json 2> gpurun_out/j_err5.err; echo "rc=$?"
+for g in 0 32 64 128; do
+GT_L2_FETCH_BYTES=$g timeout 300 python bench.py --workload c2q --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/j_c2q_l2_$g.json 2> gpurun_out/j_c2q_l2_$g.err
+done
+GT_L2_FETCH_BYTES=32 timeout 300 python bench.py --workload c3 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/j_c3_l2_32.json 2> gpurun_out/j_c3_l2_32.err
+python - <<'PY'
+import ctypes, torch
+rt = ctypes.CDLL("libcudart.so")
+v = ctypes.c_size_t(0)
+print("default L2 fetch granularity:", rt.cudaDeviceGetLimit(ctypes.byref(v), 0x05), v.value)
+PY
