@@ -125,6 +125,9 @@ SIGNATURES = {
     "gt_sketch_destroy": (None, [C.c_void_p]),
     "gt_sketch_add_sequences": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     "gt_sketch_add_hashes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "gt_sketch_live_count": (C.c_int64, [C.c_void_p]),
+    "gt_sketch_export_dev": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "gt_sketch_add_hashes_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "gt_sketch_merge": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gt_sketch_size": (C.c_int64, [C.c_void_p]),
     "gt_sketch_mins": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_uint64]),

@@ -208,9 +208,28 @@ class Sketch:
         world = dist.get_world_size(group)
         if world == 1:
             return
-        mine = self.mins()
         backend = dist.get_backend(group)
-        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        me = dist.get_rank(group)
+        if backend == "nccl":
+            # the sets never leave the devices: count, export, all-gather, add
+            L = _capi.lib()
+            dev = torch.device("cuda", torch.cuda.current_device())
+            n_mine = _capi.check(L.gt_sketch_live_count(self._h), "gt_sketch_live_count")
+            ns = torch.zeros(world, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(ns, torch.tensor([n_mine], dtype=torch.int64, device=dev), group=group)
+            ns = [int(x) for x in ns.cpu()]
+            cap = max(1, max(ns))
+            buf = torch.zeros(cap, dtype=torch.int64, device=dev)
+            _capi.check(L.gt_sketch_export_dev(self._h, buf.data_ptr(), cap), "gt_sketch_export_dev")
+            bufs = torch.empty(world * cap, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(bufs, buf, group=group)
+            torch.cuda.synchronize()
+            for q in range(world):
+                if q != me and ns[q]:
+                    _capi.check(L.gt_sketch_add_hashes_dev(self._h, bufs.data_ptr() + 8 * q * cap, ns[q]), "gt_sketch_add_hashes_dev")
+            return
+        mine = self.mins()
+        dev = torch.device("cpu")
         n = torch.tensor([mine.size], dtype=torch.int64, device=dev)
         ns = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
         dist.all_gather(ns, n, group=group)
@@ -219,10 +238,9 @@ class Sketch:
         buf[:mine.size] = torch.from_numpy(mine.view(np.int64)).to(dev)
         bufs = [torch.zeros(cap, dtype=torch.int64, device=dev) for _ in range(world)]
         dist.all_gather(bufs, buf, group=group)
-        me = dist.get_rank(group)
         for q in range(world):
             if q != me and int(ns[q].item()):
-                self.add_hashes(bufs[q][:int(ns[q].item())].cpu().numpy().view(np.uint64))
+                self.add_hashes(bufs[q][:int(ns[q].item())].numpy().view(np.uint64))
 
     def close(self):
         if getattr(self, "_h", None):

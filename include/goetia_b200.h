@@ -428,6 +428,12 @@ int64_t gt_sketch_add_sequences_dev(gt_sketch* sk, const void* d_bases, const vo
                                     uint64_t n_bases);
 /* MinHash::add_hash / merge (sourmash.hpp:80, :97) */
 int gt_sketch_add_hashes(gt_sketch* sk, const uint64_t* hashes, uint64_t n);
+/* Device-resident forms for the union of a sharded sketch (every rank sketches its reads; the sets are united by
+ * all-gather): the number of hashes the set holds now, the hashes (unsorted) into a device buffer, and hashes added
+ * from a device buffer. */
+int64_t gt_sketch_live_count(gt_sketch* sk);
+int64_t gt_sketch_export_dev(gt_sketch* sk, uint64_t* d_out, uint64_t capacity);
+int gt_sketch_add_hashes_dev(gt_sketch* sk, const uint64_t* d_hashes, uint64_t n);
 int gt_sketch_merge(gt_sketch* dst, gt_sketch* src);
 /* MinHash::size / mins (sourmash.hpp:116, :151-157): ascending, duplicate-free. */
 int64_t gt_sketch_size(gt_sketch* sk);
