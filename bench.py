@@ -454,14 +454,16 @@ def main():
 def insert_roofline(prof_ms, prof_n, step_ms_total, kmers, n_tables, peak, peak_src, workload, r_rand=None, table_bytes=0):
     """HBM roofline of the insert (64 B algorithmic per (k-mer, table)).
 
-    On the write-combined path the insert is the kernel PAIR k_bucket (hash + bucket by table slice) ->
-    k_apply (read-modify-write of the L2-resident slice); the two run concurrently on two streams (k_apply of
-    one entry store beside k_bucket filling the other), so their CUDA-event times overlap and each is inflated
-    by the other.  `achieved` is therefore the conservative figure: algorithmic bytes over the WHOLE timed
-    region (= value x 256 B); the per-kernel event times are listed under `kernels`.  `traffic` is the DRAM
-    bytes ncu measured for one launch pair (profiles/traffic.json) -- far below the algorithmic bytes, which is
-    the point of write-combining and why `frac` can exceed 1: the limiters are instruction issue (k_bucket) and
-    L2 atomic throughput (k_apply), see `dram_frac` and DESIGN.md section 3."""
+    On the write-combined path the insert is three kernels: k_bucket (hash + partition by 32 MB table slice) ->
+    k_rebucket2 (partition a slice's entries by 128 KB window) -> k_apply_win (build the window in shared memory,
+    merge it into the table with one coalesced read-modify-write).  The apply of one entry store is queued on a
+    second stream beside k_bucket filling the other store; all three kernels are persistent / SM-filling, so their
+    CUDA-event times overlap and inflate each other.  `achieved` is therefore the conservative figure: algorithmic
+    bytes over the WHOLE timed region (= value x 256 B); the per-kernel event times are listed under `kernels`.
+    `traffic` is the DRAM bytes ncu measured for one apply cycle (profiles/traffic.json: two k_bucket launches + one
+    k_rebucket2 + one k_apply_win = 103 GB per 1.33e9 k-mers = 77 B/k-mer) -- far below the 256 algorithmic bytes, which
+    is the point of write-combining and why `frac` can exceed 1; `dram_frac` is what the path really draws from HBM
+    (measured bytes per k-mer x k-mers/s over the copy peak), see DESIGN.md section 3."""
     names = ("k_bucket", "k_apply (k_rebucket + k_apply_win)", "k_walk", "k_rebucket", "k_apply_win")
     algo_bytes = ALGO_BYTES_PER_KMER_PER_TABLE * n_tables
     combined = bool(prof_n[1])
@@ -596,6 +598,9 @@ def query_arm(args, torch, gb, _capi, L, dev, local_rank, storage, graph, subs, 
         if t:
             roofline["traffic"] = float(t["k_walk"])
             roofline["traffic_detail"] = t
+            # what the random lookups really draw from HBM (the access granule is larger than the 32 B sector)
+            roofline["dram_bytes_per_kmer_measured"] = float(t["k_walk"]) / float(t["kmers_per_launch"])
+            roofline["dram_frac"] = roofline["dram_bytes_per_kmer_measured"] * value / 1e9 / peak
     except Exception:
         pass
 
@@ -633,7 +638,7 @@ def query_arm(args, torch, gb, _capi, L, dev, local_rank, storage, graph, subs, 
     return 0
 
 
-def nvlink_report(nv0, nv1, kmers_rank_total, n_tables, world, ms, peer_bytes=0):
+def nvlink_report(nv0, nv1, kmers_rank_total, n_tables, world, ms, peer_bytes=0, shipped_bytes=0):
     """NVLink traffic of rank 0's GPU over the timed region (nvidia-smi counters) beside the algorithmic figure of
     SURVEY.md section 8d: n_tables x 4 B x (G-1)/G egress per k-mer hashed on this rank."""
     algo = kmers_rank_total * n_tables * 4 * (world - 1) / world
@@ -653,6 +658,12 @@ def nvlink_report(nv0, nv1, kmers_rank_total, n_tables, world, ms, peer_bytes=0)
                     "peer_store_frac_of_link_peak": peer_bytes / (ms / 1e3) / 1e9 / 900.0 if ms > 0 else None,
                     "peer_store_source": "software counter: cursors of the buckets rank 0's k_bucket filled in peers' HBM "
                                          "(entries x 4 B, 16-byte run padding included), summed over the timed region"})
+    if shipped_bytes:
+        out.update({"copy_engine_bytes_rank0": shipped_bytes, "copy_engine_bytes_per_kmer": shipped_bytes / kmers_rank_total if kmers_rank_total else None,
+                    "copy_engine_GBps": shipped_bytes / (ms / 1e3) / 1e9 if ms > 0 else None,
+                    "copy_engine_frac_of_link_peak": shipped_bytes / (ms / 1e3) / 1e9 / 900.0 if ms > 0 else None,
+                    "copy_engine_source": "ce transport: bytes rank 0 handed to the copy engines over the timed region (whole bucket "
+                                          "regions at their capacity + the overflow lists; peer_store_bytes is the part that was filled)"})
     return out
 
 
@@ -672,7 +683,9 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
     round_bases = int(os.environ.get("GT_BENCH_ROUND_BASES", SUB_BATCH_BASES))
     rounds = max(2, -(-max_rank_reads * read_len // round_bases))
     per_round = -(-max_rank_reads // rounds)
-    st = ShardedStorage(kind, sizes, per_round * read_len)
+    # equal-length reads: the k-mer count of every round is known, so the round budget (which sizes the exchange buffers
+    # and, with the ce transport, the bytes the copy engines ship) is given in k-mers and every batch carries its count
+    st = ShardedStorage(kind, sizes, per_round * kpr)
     # rank r holds a contiguous range of the SAME global read set the single-GPU run (and the CPU reference) sees
     first_read = rank * (total_reads // world) + min(rank, total_reads % world)
     gold = golden_entry(args.workload, total_reads, WORKLOADS[args.workload][4])
@@ -695,7 +708,7 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
         for b, n in subs:
             if n:
                 st.bucket_sequences_dev_async(_capi.SHIFTER_CAN, K, b.data_ptr(), offs.data_ptr(), n, n * read_len,
-                                              d_total.data_ptr())
+                                              d_total.data_ptr(), n_kmers_upper=n * kpr)
             st.exchange_and_apply()
 
     kmers_rank = reads_rank * kpr
@@ -712,6 +725,7 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
     torch.cuda.synchronize()
     _capi.check(L.gt_profile_enable(1), "gt_profile_enable")
     st.peer_store_bytes(reset=True)
+    st.shipped_bytes = 0
     nv0 = nvlink_counters(local_rank) if rank == 0 else None  # before the barrier: not inside the timed region
     dist.barrier()
     torch.cuda.synchronize()
@@ -728,6 +742,7 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
     torch.cuda.synchronize()
     nv1 = nvlink_counters(local_rank) if rank == 0 else None
     peer_bytes = st.peer_store_bytes()
+    shipped_bytes = st.shipped_bytes
     dist.barrier()
     t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -798,7 +813,8 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
                     if n:
                         # equal-length reads: the first r1-r0+1 offsets describe any piece
                         st.bucket_packed_dev_async(_capi.SHIFTER_CAN, K, dw.data_ptr() + w0 * 8, w1 - w0 + 1, do.data_ptr(),
-                                                   df.data_ptr() + r0, r1 - r0, (r1 - r0) * read_len, d_total.data_ptr())
+                                                   df.data_ptr() + r0, r1 - r0, (r1 - r0) * read_len, d_total.data_ptr(),
+                                                   n_kmers_upper=(r1 - r0) * kpr)
                 free = torch.cuda.Event()
                 free.record(st.stream)
                 consumed[i & 1] = free
@@ -844,6 +860,9 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
                            "k_bucket stores foreign buckets straight into the owner's HBM over NVLink (CUDA IPC peer "
                            "memory), one small NCCL all-to-all of fill counts per round; k_apply of round i overlaps "
                            "k_bucket of round i+1" if st.transport == "p2p" else
+                           "k_bucket writes foreign buckets to local staging areas, the copy engines ship them into the "
+                           "owners' HBM over NVLink (CUDA IPC peer memory) while the SMs apply round i-1 and hash round i+1; "
+                           "one small NCCL all-to-all of fill counts per round" if st.transport == "ce" else
                            "one NCCL all-to-all of bucket regions per round; k_apply of round i overlaps k_bucket of "
                            "round i+1"),
                        "transport": st.transport,
@@ -861,7 +880,7 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
                          "kernels": {name: {"launches": int(prof_n[i]), "ms_total": float(prof_ms[i]),
                                             "share_of_step": float(prof_ms[i] / ms) if ms > 0 else 0.0}
                                      for i, name in enumerate(("k_bucket", "k_apply", "k_walk", "k_rebucket", "k_apply_win")) if prof_n[i]}},
-            "nvlink": nvlink_report(nv0, nv1, kmers_rank * args.steps, n_tables, world, ms, peer_bytes),
+            "nvlink": nvlink_report(nv0, nv1, kmers_rank * args.steps, n_tables, world, ms, peer_bytes, shipped_bytes),
             "cpu_baseline": None,
             "check": check,
         }

@@ -263,6 +263,7 @@ struct gt_storage {
     int rank = 0, world = 1;
     uint64_t own_lo[MAX_TABLES], own_hi[MAX_TABLES];
     void* slab[MAX_TABLES];
+    uint64_t hint_kmers = 0;           // gt_storage_hint_kmers: bound for the next device-resident batch (0 = none)
 };
 
 static uint64_t ref_table_bytes(int kind, uint64_t size) {
@@ -278,6 +279,13 @@ static uint64_t range_bytes(int kind, uint64_t lo, uint64_t hi, bool last) {
     return last ? hi / 2 + 1 - lo / 2 : n / 2;
 }
 static int slots_per_word(int kind) { return kind == GT_STORAGE_BIT ? 32 : kind == GT_STORAGE_BYTE ? 4 : 8; }
+
+// gt_storage_hint_kmers: the caller's bound for the next device-resident batch, used once
+static uint64_t take_kmer_hint(gt_storage* st, uint64_t n_bases) {
+    const uint64_t h = st->hint_kmers;
+    st->hint_kmers = 0;
+    return h && h < n_bases ? h : n_bases;
+}
 
 struct PlanHost;
 static int make_plan(int kind, const uint64_t* sizes, int n, int world, uint64_t budget, int slice_log2_bytes, PlanHost& P);
@@ -1002,9 +1010,10 @@ static int insert_sequences_dev_queue(gt_storage* st, int shifter, int K, const 
         k_kmer_counts<<<grid_for(n_reads, 256, 16), 256, 0, s>>>(offs, n_reads, K, view.d_flags, nullptr, nullptr, d_tot); ++g_launches;
         CU(cudaGetLastError());
     }
-    // n_bases bounds the k-mers of the batch without a round trip to the host
-    if (bucket_usable(st, mode, K, n_bases, n_bases)) {
-        if (bucket_insert(st, shifter, view, K, n_bases)) return -1;
+    // n_bases bounds the k-mers of the batch without a round trip to the host (or the caller's tighter bound)
+    const uint64_t kmers_upper = take_kmer_hint(st, n_bases);
+    if (bucket_usable(st, mode, K, kmers_upper, kmers_upper)) {
+        if (bucket_insert(st, shifter, view, K, kmers_upper)) return -1;
     } else if (launch_insert(st, shifter, view, K, mode, nullptr, s)) {
         return -1;
     }
@@ -1207,8 +1216,9 @@ extern "C" int gt_insert_packed_dev_async(gt_storage* st, int shifter, int K, co
                                                                  static_cast<unsigned long long*>(d_kmer_total)); ++g_launches;
         CU(cudaGetLastError());
     }
-    if (bucket_usable(st, mode, K, n_bases, n_bases)) {
-        if (bucket_insert(st, shifter, view, K, n_bases)) return -1;
+    const uint64_t kmers_upper = take_kmer_hint(st, n_bases);
+    if (bucket_usable(st, mode, K, kmers_upper, kmers_upper)) {
+        if (bucket_insert(st, shifter, view, K, kmers_upper)) return -1;
     } else if (launch_insert(st, shifter, view, K, mode, nullptr, s)) {
         return -1;
     }
@@ -1422,19 +1432,17 @@ extern "C" int gt_shard_peer_layout(int kind, const uint64_t* tablesizes, int n_
     return P.nb;
 }
 
-extern "C" int gt_storage_attach_peers(gt_storage* st, int which, void* const* inbox_of_rank, void* fill_send,
-                                        void* fill_recv) {
-    if (ensure_ctx()) return -1;
-    if (!st || !st->pend || st->world < 2) return fail("gt_storage_attach_peers: not a sharded storage");
-    if (which < 0 || which > 1) return fail("gt_storage_attach_peers: buffer set 0 or 1");
-    if (!inbox_of_rank || !fill_send || !fill_recv) return fail("gt_storage_attach_peers: NULL buffer");
+// Common part of the peer transports: region_of_rank[q] / ovf_of_rank[q] = where this rank's entries / overflow records
+// for owner q are written by k_bucket (peer memory, or a local staging area the caller ships); own_inbox = this rank's
+// inbox (world regions of R_me entries + world overflow lists), which the apply reads.
+static int attach_producer_areas(gt_storage* st, int which, const char* who, uint32_t* const* region_of_rank,
+                                 unsigned long long* const* ovf_of_rank, const void* own_inbox, void* fill_send, void* fill_recv,
+                                 bool staged) {
     Pending* p = st->pend;
     Pending::Store& S = p->store[which];
-    if (S.built) return fail("gt_storage_attach_peers: buffer set %d already attached", which);
+    if (S.built) return fail("%s: buffer set %d already attached", who, which);
     const PlanHost& H = p->host;
     const int nb = H.nb, W = st->world, me = st->rank;
-    for (int q = 0; q < W; ++q)
-        if (!inbox_of_rank[q]) return fail("gt_storage_attach_peers: inbox of rank %d is NULL", q);
     std::vector<int> owned;
     std::vector<uint64_t> R, in_region;
     peer_layout(H, R, in_region);
@@ -1446,18 +1454,16 @@ extern "C" int gt_storage_attach_peers(gt_storage* st, int which, void* const* i
         if (cudaMalloc(&S.d_bptr, nb * sizeof(uint32_t*)) != cudaSuccess ||
             cudaMalloc(&S.d_items, (size_t)n_owned * W * sizeof(ApplyItem)) != cudaSuccess) {
             cudaGetLastError();
-            return fail("gt_storage_attach_peers: out of device memory");
+            return fail("%s: out of device memory", who);
         }
     }
-    // bucket b, produced here, lands in region `me` of its owner's inbox
     std::vector<uint32_t*> ptrs(nb);
-    for (int b = 0; b < nb; ++b)
-        ptrs[b] = static_cast<uint32_t*>(inbox_of_rank[H.owner[b]]) + (uint64_t)me * R[H.owner[b]] + in_region[b];
+    for (int b = 0; b < nb; ++b) ptrs[b] = region_of_rank[H.owner[b]] + in_region[b];
     CU(cudaMemcpy(S.d_bptr, ptrs.data(), nb * sizeof(uint32_t*), cudaMemcpyHostToDevice));
     std::vector<ApplyItem> items;
     items.reserve((size_t)n_owned * W);
     const uint32_t* fr = static_cast<const uint32_t*>(fill_recv);
-    const uint32_t* mine = static_cast<const uint32_t*>(inbox_of_rank[me]);
+    const uint32_t* mine = static_cast<const uint32_t*>(own_inbox);
     for (int j = 0; j < n_owned; ++j) {
         const int b = owned[j];
         for (int q = 0; q < W; ++q)
@@ -1467,7 +1473,7 @@ extern "C" int gt_storage_attach_peers(gt_storage* st, int which, void* const* i
     if (pending_set_items(p, items, which)) return -1;
     S.d_bfill = static_cast<uint32_t*>(fill_send);
     p->own_bfill = false;
-    // overflow lists: mine in every owner's inbox (to post to), the world lists of my own inbox (to apply)
+    // overflow lists: mine for every owner (to post to), the world lists of my own inbox (to apply)
     p->ovf_cap = (uint32_t)ovf_records();
     p->count_stride = (uint32_t)n_owned + 1;
     if (!p->d_bowner) {
@@ -1476,19 +1482,91 @@ extern "C" int gt_storage_attach_peers(gt_storage* st, int which, void* const* i
         CU(cudaMalloc(&p->d_bowner, nb));
         CU(cudaMemcpy(p->d_bowner, own.data(), nb, cudaMemcpyHostToDevice));
     }
-    std::vector<unsigned long long*> lists(W);
-    for (int q = 0; q < W; ++q)
-        lists[q] = reinterpret_cast<unsigned long long*>(static_cast<char*>(inbox_of_rank[q]) + inbox_ovf_offset_bytes(H, q)) +
-                   (uint64_t)me * p->ovf_cap;
     CU(cudaMalloc(&S.d_ovf_ptr, W * sizeof(unsigned long long*)));
-    CU(cudaMemcpy(S.d_ovf_ptr, lists.data(), W * sizeof(unsigned long long*), cudaMemcpyHostToDevice));
-    S.my_ovf = reinterpret_cast<const unsigned long long*>(static_cast<const char*>(inbox_of_rank[me]) + inbox_ovf_offset_bytes(H, me));
+    CU(cudaMemcpy(S.d_ovf_ptr, ovf_of_rank, W * sizeof(unsigned long long*), cudaMemcpyHostToDevice));
+    S.my_ovf = reinterpret_cast<const unsigned long long*>(static_cast<const char*>(own_inbox) + inbox_ovf_offset_bytes(H, me));
     S.ovf_counts = fr + n_owned;
     S.fill_words = (uint32_t)(nb + W);
     CU(cudaMemset(S.d_bfill, 0, (size_t)S.fill_words * 4));
     p->entries_total = (uint64_t)W * R[me];
+    p->staged = staged;
     S.built = true;
     p->attached = true;
+    return 0;
+}
+
+extern "C" int gt_storage_attach_peers(gt_storage* st, int which, void* const* inbox_of_rank, void* fill_send,
+                                        void* fill_recv) {
+    if (ensure_ctx()) return -1;
+    if (!st || !st->pend || st->world < 2) return fail("gt_storage_attach_peers: not a sharded storage");
+    if (which < 0 || which > 1) return fail("gt_storage_attach_peers: buffer set 0 or 1");
+    if (!inbox_of_rank || !fill_send || !fill_recv) return fail("gt_storage_attach_peers: NULL buffer");
+    const PlanHost& H = st->pend->host;
+    const int W = st->world, me = st->rank;
+    for (int q = 0; q < W; ++q)
+        if (!inbox_of_rank[q]) return fail("gt_storage_attach_peers: inbox of rank %d is NULL", q);
+    // bucket b, produced here, lands in region `me` of its owner's inbox; so does this rank's overflow list
+    std::vector<uint32_t*> regions(W);
+    std::vector<unsigned long long*> lists(W);
+    const uint64_t cap = ovf_records();
+    for (int q = 0; q < W; ++q) {
+        regions[q] = static_cast<uint32_t*>(inbox_of_rank[q]) + (uint64_t)me * inbox_region_entries(H, q);
+        lists[q] = reinterpret_cast<unsigned long long*>(static_cast<char*>(inbox_of_rank[q]) + inbox_ovf_offset_bytes(H, q)) + (uint64_t)me * cap;
+    }
+    return attach_producer_areas(st, which, "gt_storage_attach_peers", regions.data(), lists.data(), inbox_of_rank[me], fill_send,
+                                 fill_recv, false);
+}
+
+// Staged peer transport (copy engines instead of SM stores): as gt_storage_attach_peers, but what this rank produces for a
+// foreign owner q is written to a LOCAL staging area -- stage_of_rank[q]: R_q entries, padded to 16 bytes, then this
+// rank's overflow list for q -- which the caller ships into q's inbox (region `rank`, overflow list `rank`) with plain
+// device-to-device copies over NVLink (gt_peer_copy_async) while the SMs go on hashing.
+extern "C" uint64_t gt_storage_stage_bytes(const gt_storage* st, int rank) {
+    if (!st || !st->pend || rank < 0 || rank >= st->world) return 0;
+    return (inbox_region_entries(st->pend->host, rank) * 4 + 15) / 16 * 16 + ovf_records() * 8;
+}
+extern "C" int gt_storage_attach_staged(gt_storage* st, int which, void* own_inbox, void* const* stage_of_rank, void* fill_send,
+                                         void* fill_recv) {
+    if (ensure_ctx()) return -1;
+    if (!st || !st->pend || st->world < 2) return fail("gt_storage_attach_staged: not a sharded storage");
+    if (which < 0 || which > 1) return fail("gt_storage_attach_staged: buffer set 0 or 1");
+    if (!own_inbox || !stage_of_rank || !fill_send || !fill_recv) return fail("gt_storage_attach_staged: NULL buffer");
+    const PlanHost& H = st->pend->host;
+    const int W = st->world, me = st->rank;
+    std::vector<uint32_t*> regions(W);
+    std::vector<unsigned long long*> lists(W);
+    const uint64_t cap = ovf_records();
+    for (int q = 0; q < W; ++q) {
+        if (q == me) {  // this rank's own buckets go where the apply reads them
+            regions[q] = static_cast<uint32_t*>(own_inbox) + (uint64_t)me * inbox_region_entries(H, me);
+            lists[q] = reinterpret_cast<unsigned long long*>(static_cast<char*>(own_inbox) + inbox_ovf_offset_bytes(H, me)) + (uint64_t)me * cap;
+            continue;
+        }
+        if (!stage_of_rank[q]) return fail("gt_storage_attach_staged: staging area for rank %d is NULL", q);
+        if (reinterpret_cast<uintptr_t>(stage_of_rank[q]) & 15) return fail("gt_storage_attach_staged: staging areas must be 16-byte aligned");
+        regions[q] = static_cast<uint32_t*>(stage_of_rank[q]);
+        lists[q] = reinterpret_cast<unsigned long long*>(static_cast<char*>(stage_of_rank[q]) + (inbox_region_entries(H, q) * 4 + 15) / 16 * 16);
+    }
+    return attach_producer_areas(st, which, "gt_storage_attach_staged", regions.data(), lists.data(), own_inbox, fill_send, fill_recv,
+                                 true);
+}
+
+// Device-to-device copy on a stream of the caller (both pointers valid in this process: local memory or a peer's
+// allocation mapped with gt_peer_open).  Runs on a copy engine, not on the SMs.
+extern "C" int gt_peer_copy_async(void* dst, const void* src, uint64_t bytes, void* stream) {
+    if (ensure_ctx()) return -1;
+    if (bytes == 0) return 0;
+    if (!dst || !src) return fail("gt_peer_copy_async: NULL pointer");
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+// Upper bound of the k-mers in the NEXT device-resident batch bucketed into this storage (gt_insert_sequences_dev[_async],
+// gt_insert_packed_dev_async), for callers that know it (equal-length reads): without it the library has to assume one
+// k-mer per base, and a sharded storage's round budget -- which sizes every exchange buffer -- has to be given in bases.
+extern "C" int gt_storage_hint_kmers(gt_storage* st, uint64_t n_kmers_upper) {
+    if (!st) return fail("gt_storage_hint_kmers: NULL storage");
+    st->hint_kmers = n_kmers_upper;
     return 0;
 }
 

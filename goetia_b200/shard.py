@@ -190,6 +190,13 @@ class ShardedStorage:
                        counts travel by collective (one small all-to-all), which doubles as the
                        "every producer has finished" signal.
     ``nccl``           k_bucket fills a local outbox; one NCCL all-to-all ships the regions.
+    ``ce``             the peer layout, but k_bucket writes foreign buckets into LOCAL staging areas
+                       (``gt_storage_attach_staged``) and the copy engines ship them into the owners' inboxes
+                       (``gt_peer_copy_async`` on copy streams) while the SMs hash the next round: NVLink costs no SM
+                       time and no CTA slots, so k_bucket and the window apply run at their single-GPU rates.  The
+                       round is finished -- fill counts exchanged, buckets applied -- one call later
+                       (``exchange_and_apply`` of the next round, or ``join`` / ``synchronize``, which are therefore
+                       COLLECTIVE with this transport: every rank must call them at the same points).
 
     Either way there are two buffer sets and two streams: k_apply of round i (apply stream)
     overlaps k_bucket of round i+1 into the other set (compute stream).
@@ -202,8 +209,8 @@ class ShardedStorage:
         self.torch, self.dist, self.group = torch, dist, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.transport = transport or os.environ.get("GT_SHARD_TRANSPORT", "p2p")
-        if self.transport not in ("p2p", "nccl"):
-            raise ValueError("transport must be 'p2p' or 'nccl'")
+        if self.transport not in ("p2p", "nccl", "ce"):
+            raise ValueError("transport must be 'p2p', 'ce' or 'nccl'")
         L = _capi.lib()
         self.kind = int(kind)
         self.plan = plan = ShardPlan(kind, sizes, self.world, budget_kmers, slice_log2_bytes)
@@ -222,6 +229,9 @@ class ShardedStorage:
         self.cur = 0
         self._applied = [None, None]   # event: k_apply of the set has finished (its buffers are free again)
         self._peer_ptrs, self._own_inbox = [], []
+        self._pending = None           # ce transport: (set, copies-landed events) of the round still to be finished
+        self._inbox_ptrs, self._stage = [], []
+        self.shipped_bytes = 0         # ce transport: bytes handed to the copy engines (whole regions + overflow lists)
         W, me = self.world, self.rank
         if self.transport == "nccl":
             self.sets = [ShardExchange(plan, me, torch, dev, group) for _ in range(2)]
@@ -265,8 +275,27 @@ class ShardedStorage:
                 self.fill_send.append(fs)
                 self.fill_recv.append(fr)
                 self._fx.append(torch.zeros(self._n_fill, dtype=torch.int32, device=dev))
-                _capi.check(L.gt_storage_attach_peers(self._h, w, ptrs, fs.data_ptr(), fr.data_ptr()),
-                            "gt_storage_attach_peers")
+                if self.transport == "ce":
+                    # local staging area per foreign owner; the copy engines ship it (exchange_and_apply)
+                    areas = [None if q == me else torch.zeros(int(L.gt_storage_stage_bytes(self._h, q)), dtype=torch.uint8, device=dev)
+                             for q in range(W)]
+                    sp = (C.c_void_p * W)()
+                    for q in range(W):
+                        sp[q] = None if q == me else areas[q].data_ptr()
+                    _capi.check(L.gt_storage_attach_staged(self._h, w, own, sp, fs.data_ptr(), fr.data_ptr()),
+                                "gt_storage_attach_staged")
+                    self._stage.append(areas)
+                    self._inbox_ptrs.append([int(ptrs[q]) for q in range(W)])
+                else:
+                    _capi.check(L.gt_storage_attach_peers(self._h, w, ptrs, fs.data_ptr(), fr.data_ptr()),
+                                "gt_storage_attach_peers")
+            if self.transport == "ce":
+                lay = plan.peer_layout()
+                self._R = [int(x) for x in lay["region"]]
+                self._ovf_off = [int(x) for x in lay["ovf_offset_bytes"]]
+                self._ovf_bytes = [(int(lay["inbox_bytes"][q]) - self._ovf_off[q]) // W for q in range(W)]
+                n_cs = max(1, min(int(os.environ.get("GT_SHARD_COPY_STREAMS", "2")), W - 1))
+                self.copy_streams = [torch.cuda.Stream() for _ in range(n_cs)]
             torch.cuda.synchronize()
             dist.barrier(group=group)  # every rank has mapped every inbox before anyone stores into one
 
@@ -274,7 +303,7 @@ class ShardedStorage:
     def handle(self):
         return self._h
 
-    def bucket_sequences_dev(self, shifter_kind, K, d_bases_ptr, d_offsets_ptr, n_reads, n_bases):
+    def bucket_sequences_dev(self, shifter_kind, K, d_bases_ptr, d_offsets_ptr, n_reads, n_bases, n_kmers_upper=None):
         """Step 1 of a round: pack + hash + bucket this rank's (device-resident) reads into the
         current buffer set (p2p: the entries of foreign slices go straight to their owners)."""
         L = _capi.lib()
@@ -282,22 +311,27 @@ class ShardedStorage:
             if self._applied[self.cur] is not None:
                 self.stream.wait_event(self._applied[self.cur])
             _capi.check(L.gt_storage_select_store(self._h, self.cur), "gt_storage_select_store")
+            if n_kmers_upper is not None:  # equal-length reads: the caller knows the k-mer count, so the round budget can be tight
+                _capi.check(L.gt_storage_hint_kmers(self._h, int(n_kmers_upper)), "gt_storage_hint_kmers")
             return int(_capi.check(L.gt_insert_sequences_dev(self._h, shifter_kind, K, d_bases_ptr, d_offsets_ptr,
                                                              n_reads, n_bases, _capi.MODE_BLIND),
                                    "gt_insert_sequences_dev"))
 
-    def bucket_sequences_dev_async(self, shifter_kind, K, d_bases_ptr, d_offsets_ptr, n_reads, n_bases, d_kmer_total_ptr=None):
+    def bucket_sequences_dev_async(self, shifter_kind, K, d_bases_ptr, d_offsets_ptr, n_reads, n_bases, d_kmer_total_ptr=None,
+                                   n_kmers_upper=None):
         """bucket_sequences_dev without the host wait (the k-mer count is added to a device uint64)."""
         L = _capi.lib()
         with self.torch.cuda.stream(self.stream):
             if self._applied[self.cur] is not None:
                 self.stream.wait_event(self._applied[self.cur])
             _capi.check(L.gt_storage_select_store(self._h, self.cur), "gt_storage_select_store")
+            if n_kmers_upper is not None:  # equal-length reads: the caller knows the k-mer count, so the round budget can be tight
+                _capi.check(L.gt_storage_hint_kmers(self._h, int(n_kmers_upper)), "gt_storage_hint_kmers")
             _capi.check(L.gt_insert_sequences_dev_async(self._h, shifter_kind, K, d_bases_ptr, d_offsets_ptr, n_reads, n_bases,
                                                         _capi.MODE_BLIND, d_kmer_total_ptr), "gt_insert_sequences_dev_async")
 
     def bucket_packed_dev_async(self, shifter_kind, K, d_words_ptr, n_words_alloc, d_offsets_ptr, d_flags_ptr, n_reads, n_bases,
-                                d_kmer_total_ptr=None):
+                                d_kmer_total_ptr=None, n_kmers_upper=None):
         """Step 1 of a round for a batch that is already 2-bit packed in HBM (the host packed it, so only 0.25 B/base
         crossed PCIe): hash + bucket, no pack kernel, no host wait."""
         L = _capi.lib()
@@ -305,31 +339,53 @@ class ShardedStorage:
             if self._applied[self.cur] is not None:
                 self.stream.wait_event(self._applied[self.cur])
             _capi.check(L.gt_storage_select_store(self._h, self.cur), "gt_storage_select_store")
+            if n_kmers_upper is not None:  # equal-length reads: the caller knows the k-mer count, so the round budget can be tight
+                _capi.check(L.gt_storage_hint_kmers(self._h, int(n_kmers_upper)), "gt_storage_hint_kmers")
             _capi.check(L.gt_insert_packed_dev_async(self._h, shifter_kind, K, d_words_ptr, n_words_alloc, d_offsets_ptr, d_flags_ptr,
                                                      n_reads, n_bases, _capi.MODE_BLIND, d_kmer_total_ptr),
                         "gt_insert_packed_dev_async")
 
     def exchange_and_apply(self):
         """Steps 2 and 3 of a round (collective: every rank calls it once per round): exchange of
-        the current set, k_apply of this rank's slices on the apply stream, switch sets."""
-        torch, dist, plan, w = self.torch, self.dist, self.plan, self.cur
-        with torch.cuda.stream(self.stream):
-            if self.transport == "nccl":
+        the current set, k_apply of this rank's slices on the apply stream, switch sets.  (ce transport: the round's
+        staging areas go to the copy engines now; its fill exchange and apply are queued by the next call.)"""
+        torch, w = self.torch, self.cur
+        if self.transport == "ce":
+            return self._ship_and_finish_previous()
+        if self.transport == "p2p":
+            # the fill exchange is stream-ordered after k_bucket on every rank, so its completion is also the signal
+            # that all peer stores have landed
+            self._finish_fills_and_apply(w)
+        else:
+            with torch.cuda.stream(self.stream):
                 self.sets[w].exchange()
-            else:
-                # Peers start storing into my OTHER set as soon as they are past this exchange, so
-                # it must not complete before that set's k_apply has finished here.
-                if self._applied[w ^ 1] is not None:
-                    self.stream.wait_event(self._applied[w ^ 1])
-                torch.index_select(self.fill_send[w], 0, self._perm, out=self._fx[w])
-                # software NVLink counter: entries this rank stored into peers' inboxes this round (cursors of foreign
-                # buckets, 16-byte run padding included); nvidia-smi's link counters are not available on every box
-                if getattr(self, "_foreign", None) is None:
-                    own = torch.as_tensor(np.asarray(plan.owner) != self.rank, device=self.device)
-                    self._foreign = own.to(torch.int64)
-                    self._peer_entries = torch.zeros(1, dtype=torch.int64, device=self.device)
-                self._peer_entries += (self.fill_send[w][:plan.nb].to(torch.int64) * self._foreign).sum()
-                dist.all_to_all_single(self.fill_recv[w], self._fx[w], self._fill_out, self._fill_in, group=self.group)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+            self.apply_stream.wait_event(ev)
+            _capi.check(_capi.lib().gt_storage_apply_store(self._h, w), "gt_storage_apply_store")
+            done = torch.cuda.Event()
+            done.record(self.apply_stream)
+            self._applied[w] = done
+        self.cur = w ^ 1
+
+    # ---- ce transport: copy engines ship round r while the SMs finish round r-1 and hash round r+1 -------------------
+    def _finish_fills_and_apply(self, w):
+        """fill-count all-to-all of set w (after this rank's copies of that set have landed) + apply (p2p and ce)."""
+        torch, dist, plan = self.torch, self.dist, self.plan
+        with torch.cuda.stream(self.stream):
+            # Peers start writing into my OTHER set as soon as they are past this exchange, so it must not complete
+            # before that set's k_apply has finished here.
+            if self._applied[w ^ 1] is not None:
+                self.stream.wait_event(self._applied[w ^ 1])
+            torch.index_select(self.fill_send[w], 0, self._perm, out=self._fx[w])
+            # software NVLink counter: entries this rank produced for peers' slices this round (cursors of foreign
+            # buckets, 16-byte run padding included); nvidia-smi's link counters are not available on every box
+            if getattr(self, "_foreign", None) is None:
+                own = torch.as_tensor(np.asarray(plan.owner) != self.rank, device=self.device)
+                self._foreign = own.to(torch.int64)
+                self._peer_entries = torch.zeros(1, dtype=torch.int64, device=self.device)
+            self._peer_entries += (self.fill_send[w][:plan.nb].to(torch.int64) * self._foreign).sum()
+            dist.all_to_all_single(self.fill_recv[w], self._fx[w], self._fill_out, self._fill_in, group=self.group)
             ev = torch.cuda.Event()
             ev.record(self.stream)
         self.apply_stream.wait_event(ev)
@@ -337,6 +393,43 @@ class ShardedStorage:
         done = torch.cuda.Event()
         done.record(self.apply_stream)
         self._applied[w] = done
+
+    def _finish_pending(self):
+        if self._pending is None:
+            return
+        w, landed = self._pending
+        self._pending = None
+        for ev in landed:
+            self.stream.wait_event(ev)  # stream order: my copies of that round are in the peers' inboxes before the all-to-all
+        self._finish_fills_and_apply(w)
+
+    def _ship_and_finish_previous(self):
+        """ce transport, round r (set w): finish round r-1 (its copies have had k_bucket of round r to land), then hand
+        round r's staging areas to the copy engines.  The copies start after the all-to-all of round r-1 has completed
+        here -- every peer has then entered it, i.e. is past its apply of round r-2, the last reader of the inbox set
+        these copies write -- and after k_bucket of round r (both by stream order: one event on the compute stream)."""
+        torch, L, w, me, W = self.torch, _capi.lib(), self.cur, self.rank, self.world
+        self._finish_pending()
+        go = torch.cuda.Event()
+        go.record(self.stream)
+        landed = []
+        for cs in self.copy_streams:
+            cs.wait_event(go)
+        for i in range(1, W):
+            q = (me + i) % W  # every rank starts with a different destination
+            cs = self.copy_streams[(i - 1) % len(self.copy_streams)]
+            src = self._stage[w][q].data_ptr()
+            dst = self._inbox_ptrs[w][q]
+            reg = self._R[q] * 4
+            _capi.check(L.gt_peer_copy_async(dst + me * reg, src, reg, cs.cuda_stream), "gt_peer_copy_async")
+            _capi.check(L.gt_peer_copy_async(dst + self._ovf_off[q] + me * self._ovf_bytes[q], src + (reg + 15) // 16 * 16,
+                                             self._ovf_bytes[q], cs.cuda_stream), "gt_peer_copy_async")
+            self.shipped_bytes += reg + self._ovf_bytes[q]
+        for cs in self.copy_streams:
+            ev = torch.cuda.Event()
+            ev.record(cs)
+            landed.append(ev)
+        self._pending = (w, landed)
         self.cur = w ^ 1
 
     def peer_store_bytes(self, reset=False):
@@ -353,11 +446,13 @@ class ShardedStorage:
     def join(self):
         """Order the compute stream after every k_apply queued so far (no host wait): an event
         recorded on ``stream`` after this covers the whole round, both streams."""
+        self._finish_pending()  # ce transport: collective
         for ev in self._applied:
             if ev is not None:
                 self.stream.wait_event(ev)
 
     def synchronize(self):
+        self._finish_pending()  # ce transport: collective
         self.stream.synchronize()
         self.apply_stream.synchronize()
 
@@ -611,12 +706,12 @@ class ShardedStorage:
         self._n_unique = 0
 
     def close(self, collective=True):
-        """Collective when the transport is p2p (barriers keep a peer from storing into, or
+        """Collective when the transport is p2p or ce (barriers keep a peer from storing into, or
         holding a mapping of, memory that is going away)."""
         if getattr(self, "_h", None):
             L = _capi.load()
             L.gt_synchronize()
-            if self.transport == "p2p" and collective:
+            if self.transport in ("p2p", "ce") and collective:
                 # nobody may still be storing into a mapping that is about to go away
                 try:
                     self.dist.barrier(group=self.group)
@@ -627,7 +722,7 @@ class ShardedStorage:
             L.gt_storage_destroy(self._h)
             for p in self._peer_ptrs:
                 L.gt_peer_close(p)
-            if self.transport == "p2p" and collective:
+            if self.transport in ("p2p", "ce") and collective:
                 try:
                     self.dist.barrier(group=self.group)  # peers have unmapped before the memory is freed
                 except Exception:

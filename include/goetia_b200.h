@@ -336,6 +336,25 @@ int gt_shard_peer_layout(int kind, const uint64_t* tablesizes, int n_tables, int
  * one small all-to-all. */
 int gt_storage_attach_peers(gt_storage* st, int which, void* const* inbox_of_rank, void* fill_send,
                             void* fill_recv);
+/* Staged peer transport (copy engines instead of SM stores; the default of goetia_b200/shard.py): the inboxes are
+ * laid out as above, but k_bucket writes what it produces for a FOREIGN owner q into a local staging area
+ * stage_of_rank[q] (gt_storage_stage_bytes(st, q) bytes, 16-byte aligned: R_q entries, padded to 16 bytes, then this
+ * rank's overflow list for q; entry `rank` of the array is ignored), and the caller ships the area into q's inbox --
+ * the R_q entries to entry rank * R_q, the list to ovf_offset_bytes[q] + rank * GT_OVF_RECORDS * 8 -- with
+ * gt_peer_copy_async on a copy stream: device-to-device copies over NVLink that run on the copy engines while the
+ * SMs hash the next round.  This rank's own buckets go straight into region `rank` of own_inbox.  fill_send /
+ * fill_recv as for gt_storage_attach_peers. */
+uint64_t gt_storage_stage_bytes(const gt_storage* st, int rank);
+int gt_storage_attach_staged(gt_storage* st, int which, void* own_inbox, void* const* stage_of_rank, void* fill_send,
+                             void* fill_recv);
+/* cudaMemcpyAsync(dst, src, bytes) on `stream` (a cudaStream_t); dst / src: local device memory or a peer's
+ * allocation mapped with gt_peer_open. */
+int gt_peer_copy_async(void* dst, const void* src, uint64_t bytes, void* stream);
+/* Upper bound of the k-mers in the NEXT device-resident batch inserted into `st` (gt_insert_sequences_dev[_async],
+ * gt_insert_packed_dev_async), used once.  Without it the library assumes one k-mer per base (it cannot read the
+ * device-resident offsets without a round trip), so a sharded storage's budget_kmers -- which sizes every exchange
+ * buffer -- would have to be given in bases; callers with equal-length reads know the exact count. */
+int gt_storage_hint_kmers(gt_storage* st, uint64_t n_kmers_upper);
 /* Storage::query restricted to the slots this rank holds (routed queries on a sharded storage):
  * counts[i] = AND / min over the tables' slots of hashes[i] that fall in this rank's ranges, the
  * neutral element (1, 255, 15) where none does; the AND / min over all ranks' answers (an

@@ -124,7 +124,7 @@ def test_owner_routed_requests_gloo(kind, world):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("transport", ["p2p", "nccl"])
+@pytest.mark.parametrize("transport", ["p2p", "ce", "nccl"])
 @pytest.mark.parametrize("kind", [0, 1, 2])
 def test_sharded_insert_nccl(kind, transport):
     import torch
@@ -139,8 +139,9 @@ def test_sharded_insert_nccl(kind, transport):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("transport", ["p2p", "ce"])
 @pytest.mark.parametrize("kind", [0, 1])
-def test_sharded_insert_foreign_bucket_overflow(kind):
+def test_sharded_insert_foreign_bucket_overflow(kind, transport):
     """Heavily duplicated reads with capacities sized for the uniform share: buckets of foreign slices overflow
     and the excess travels through the overflow lists (bucket.cuh, post_foreign) -- tables stay bit-exact."""
     import torch
@@ -148,6 +149,6 @@ def test_sharded_insert_foreign_bucket_overflow(kind):
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     rcs, outs = launch("cuda", kind, 2, {"SHARD_TABLE_X": "40000000", "SHARD_READS": "40000", "SHARD_SLICE_LOG2": "16",
-                                         "SHARD_ROUNDS": "2", "SHARD_TRANSPORT": "p2p", "SHARD_BUDGET_X": "1"})
+                                         "SHARD_ROUNDS": "2", "SHARD_TRANSPORT": transport, "SHARD_BUDGET_X": "1"})
     assert rcs == [0, 0], "\n".join(outs)
     assert "tables bit-exact" in outs[0]
