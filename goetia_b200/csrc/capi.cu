@@ -492,12 +492,14 @@ template <int OP, int KIND, bool CAN, bool TRACK, int NT>
 static int launch_walk_t(const WalkArgs& a, const TableSet& ts, cudaStream_t s) {
     auto kern = k_walk<OP, KIND, CAN, TRACK, NT>;
     static int occ = 0;
+    static size_t occ_smem = 0;  // the occupancy depends on K through the halo: cached per shared-memory size
     const int halo_words = ((a.K - 1 + 31) >> 5) + 1;
     const size_t smem = (16 + TILE_THREADS + halo_words) * sizeof(uint64_t);
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (!occ) {
+    if (!occ || occ_smem != smem) {
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TILE_THREADS, smem));
         if (occ < 1) occ = 1;
+        occ_smem = smem;
     }
     uint64_t n_tiles = (a.n_bases + TILE_POS - 1) / TILE_POS;
     if (a.tile_n) n_tiles = std::min(n_tiles - std::min(n_tiles, a.tile_lo), a.tile_n);

@@ -177,10 +177,15 @@ class dBG:
                                                                    d_bases_ptr, d_offsets_ptr, n_reads, n_bases,
                                                                    mode), "gt_insert_sequences_dev"))
 
-    def insert_sequences_dev_async(self, d_bases_ptr, d_offsets_ptr, n_reads, n_bases, mode=None, d_kmer_total_ptr=None):
+    def insert_sequences_dev_async(self, d_bases_ptr, d_offsets_ptr, n_reads, n_bases, mode=None, d_kmer_total_ptr=None,
+                                   n_kmers_upper=None):
         """insert_sequences_dev without the host wait: queued on the library's compute stream; the k-mers
-        consumed are added to the device uint64 at d_kmer_total_ptr (optional)."""
+        consumed are added to the device uint64 at d_kmer_total_ptr (optional).  n_kmers_upper: the caller's bound on the
+        batch's k-mers (equal-length reads know it exactly); without it the library assumes one k-mer per base when it
+        decides how many batches fit a pending store before the store has to be applied."""
         mode = self.mode if mode is None else mode
+        if n_kmers_upper is not None:
+            _capi.check(_capi.lib().gt_storage_hint_kmers(self.S.handle, int(n_kmers_upper)), "gt_storage_hint_kmers")
         _capi.check(_capi.lib().gt_insert_sequences_dev_async(self.S.handle, self.hasher.shifter_kind, self.K, d_bases_ptr,
                                                               d_offsets_ptr, n_reads, n_bases, mode, d_kmer_total_ptr),
                     "gt_insert_sequences_dev_async")

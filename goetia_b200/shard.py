@@ -184,13 +184,13 @@ class ShardedStorage:
 
     Two transports move the buckets of foreign slices to their owners:
 
-    ``p2p`` (default)  k_bucket stores every run of entries straight into the owner's inbox over
+    ``p2p``            k_bucket stores every run of entries straight into the owner's inbox over
                        NVLink (peer memory mapped with CUDA IPC, ``gt_storage_attach_peers``): the
                        transfer is fused with the hashing, run by run.  Only the per-bucket fill
                        counts travel by collective (one small all-to-all), which doubles as the
                        "every producer has finished" signal.
     ``nccl``           k_bucket fills a local outbox; one NCCL all-to-all ships the regions.
-    ``ce``             the peer layout, but k_bucket writes foreign buckets into LOCAL staging areas
+    ``ce`` (default)   the peer layout, but k_bucket writes foreign buckets into LOCAL staging areas
                        (``gt_storage_attach_staged``) and the copy engines ship them into the owners' inboxes
                        (``gt_peer_copy_async`` on copy streams) while the SMs hash the next round: NVLink costs no SM
                        time and no CTA slots, so k_bucket and the window apply run at their single-GPU rates.  The
@@ -208,7 +208,7 @@ class ShardedStorage:
         import torch.distributed as dist
         self.torch, self.dist, self.group = torch, dist, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        self.transport = transport or os.environ.get("GT_SHARD_TRANSPORT", "p2p")
+        self.transport = transport or os.environ.get("GT_SHARD_TRANSPORT", "ce")
         if self.transport not in ("p2p", "nccl", "ce"):
             raise ValueError("transport must be 'p2p', 'ce' or 'nccl'")
         L = _capi.lib()
@@ -294,7 +294,7 @@ class ShardedStorage:
                 self._R = [int(x) for x in lay["region"]]
                 self._ovf_off = [int(x) for x in lay["ovf_offset_bytes"]]
                 self._ovf_bytes = [(int(lay["inbox_bytes"][q]) - self._ovf_off[q]) // W for q in range(W)]
-                n_cs = max(1, min(int(os.environ.get("GT_SHARD_COPY_STREAMS", "2")), W - 1))
+                n_cs = max(1, min(int(os.environ.get("GT_SHARD_COPY_STREAMS", "4")), W - 1))
                 self.copy_streams = [torch.cuda.Stream() for _ in range(n_cs)]
             torch.cuda.synchronize()
             dist.barrier(group=group)  # every rank has mapped every inbox before anyone stores into one

@@ -227,11 +227,13 @@ class _Storage:
             pos += nb
         L = _capi.lib()
         if sizes != self.get_tablesizes():
-            L.gt_storage_destroy(self._h)
-            self._sizes = np.asarray(sizes, dtype=np.uint64)
-            self._h = L.gt_storage_create(self.kind, self._sizes.ctypes.data_as(_capi.u64p), len(sizes))
-            if not self._h:
+            # build the replacement first and swap only on success: a failed create must not leave a freed handle behind
+            new_sizes = np.asarray(sizes, dtype=np.uint64)
+            h = L.gt_storage_create(self.kind, new_sizes.ctypes.data_as(_capi.u64p), len(sizes))
+            if not h:
                 raise GoetiaException("gt_storage_create: " + _capi.last_error())
+            old, self._h, self._sizes = self._h, h, new_sizes
+            L.gt_storage_destroy(old)
         for i, t in enumerate(tables):
             t = np.ascontiguousarray(t)
             _capi.check(L.gt_storage_upload_table(self._h, i, t.ctypes.data), "gt_storage_upload_table")

@@ -82,7 +82,7 @@ def test_host_cursor_shifter_matches_golden(golden):
 def test_bin_of_arithmetic_is_exact():
     """The cheap reduction k_bucket uses for big tables equals h % d for every divisor class and edge value."""
     import random
-    from goetia_b200.csrc_check import bin_of_host, fastmod_host
+    from tests.csrc_check import bin_of_host, fastmod_host
     rnd = random.Random(7)
     ds = [2**28, 2**28 + 1, 2**29 - 3, 999999937, 2**30 + 7, 2**31 - 1, 2**31, 3999999979, 2**32 - 1, 2**32, 2**32 + 1,
           7999999957, 2**33 - 9, 2**40 + 15, 2**58, 2**28 - 1, 999983, 2**58 + 1]

@@ -116,7 +116,7 @@ def test_hash_vector_members_and_fastmod_edges(gb, kind, _n):
     assert_tables_equal(st.get_raw_tables(), ref.tables())
     assert np.array_equal(st.query_many(hs), ref.query_hashes(hs))
     big = [2**40 + 15, 2**62 + 1, 2**63]  # table sizes beyond 2^32: only the arithmetic is exercised
-    from goetia_b200.csrc_check import fastmod_host
+    from tests.csrc_check import fastmod_host
     for d in big + sizes:
         for h in edge.tolist() + hs[:200].tolist():
             assert fastmod_host(int(h), d) == int(h) % d
