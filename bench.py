@@ -738,6 +738,8 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
     _capi.check(L.gt_profile_enable(1), "gt_profile_enable")
     st.peer_store_bytes(reset=True)
     st.shipped_bytes = 0
+    if getattr(st, "_copy_prof", None) is not None:
+        st._copy_prof = []
     nv0 = nvlink_counters(local_rank) if rank == 0 else None  # before the barrier: not inside the timed region
     dist.barrier()
     torch.cuda.synchronize()
@@ -755,6 +757,7 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
     nv1 = nvlink_counters(local_rank) if rank == 0 else None
     peer_bytes = st.peer_store_bytes()
     shipped_bytes = st.shipped_bytes
+    copy_prof = st.copy_profile() if hasattr(st, "copy_profile") else None
     dist.barrier()
     t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -892,7 +895,8 @@ def multi_gpu_arm(args, rank, world, local_rank, torch, gb, _capi, sizes, total_
                          "kernels": {name: {"launches": int(prof_n[i]), "ms_total": float(prof_ms[i]),
                                             "share_of_step": float(prof_ms[i] / ms) if ms > 0 else 0.0}
                                      for i, name in enumerate(("k_bucket", "k_apply", "k_walk", "k_rebucket", "k_apply_win")) if prof_n[i]}},
-            "nvlink": nvlink_report(nv0, nv1, kmers_rank * args.steps, n_tables, world, ms, peer_bytes, shipped_bytes),
+            "nvlink": dict(nvlink_report(nv0, nv1, kmers_rank * args.steps, n_tables, world, ms, peer_bytes, shipped_bytes),
+                           **({"copy_engine_profile_rank0": copy_prof} if copy_prof else {})),
             "cpu_baseline": None,
             "check": check,
         }

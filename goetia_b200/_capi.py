@@ -94,6 +94,7 @@ SIGNATURES = {
     "gt_storage_attach_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gt_storage_stage_bytes": (C.c_uint64, [C.c_void_p, C.c_int]),
     "gt_storage_attach_staged": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gt_storage_attach_areas": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gt_peer_copy_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "gt_storage_hint_kmers": (C.c_int, [C.c_void_p, C.c_uint64]),
     "gt_query_hashes_local_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),

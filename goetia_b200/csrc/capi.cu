@@ -1527,12 +1527,12 @@ extern "C" uint64_t gt_storage_stage_bytes(const gt_storage* st, int rank) {
     if (!st || !st->pend || rank < 0 || rank >= st->world) return 0;
     return (inbox_region_entries(st->pend->host, rank) * 4 + 15) / 16 * 16 + ovf_records() * 8;
 }
-extern "C" int gt_storage_attach_staged(gt_storage* st, int which, void* own_inbox, void* const* stage_of_rank, void* fill_send,
-                                         void* fill_recv) {
+extern "C" int gt_storage_attach_areas(gt_storage* st, int which, void* own_inbox, void* const* region_of_rank,
+                                        void* const* ovf_of_rank, void* fill_send, void* fill_recv) {
     if (ensure_ctx()) return -1;
-    if (!st || !st->pend || st->world < 2) return fail("gt_storage_attach_staged: not a sharded storage");
-    if (which < 0 || which > 1) return fail("gt_storage_attach_staged: buffer set 0 or 1");
-    if (!own_inbox || !stage_of_rank || !fill_send || !fill_recv) return fail("gt_storage_attach_staged: NULL buffer");
+    if (!st || !st->pend || st->world < 2) return fail("gt_storage_attach_areas: not a sharded storage");
+    if (which < 0 || which > 1) return fail("gt_storage_attach_areas: buffer set 0 or 1");
+    if (!own_inbox || !region_of_rank || !ovf_of_rank || !fill_send || !fill_recv) return fail("gt_storage_attach_areas: NULL buffer");
     const PlanHost& H = st->pend->host;
     const int W = st->world, me = st->rank;
     std::vector<uint32_t*> regions(W);
@@ -1544,13 +1544,29 @@ extern "C" int gt_storage_attach_staged(gt_storage* st, int which, void* own_inb
             lists[q] = reinterpret_cast<unsigned long long*>(static_cast<char*>(own_inbox) + inbox_ovf_offset_bytes(H, me)) + (uint64_t)me * cap;
             continue;
         }
-        if (!stage_of_rank[q]) return fail("gt_storage_attach_staged: staging area for rank %d is NULL", q);
-        if (reinterpret_cast<uintptr_t>(stage_of_rank[q]) & 15) return fail("gt_storage_attach_staged: staging areas must be 16-byte aligned");
-        regions[q] = static_cast<uint32_t*>(stage_of_rank[q]);
-        lists[q] = reinterpret_cast<unsigned long long*>(static_cast<char*>(stage_of_rank[q]) + (inbox_region_entries(H, q) * 4 + 15) / 16 * 16);
+        if (!region_of_rank[q] || !ovf_of_rank[q]) return fail("gt_storage_attach_areas: area for rank %d is NULL", q);
+        if ((reinterpret_cast<uintptr_t>(region_of_rank[q]) & 15) || (reinterpret_cast<uintptr_t>(ovf_of_rank[q]) & 7))
+            return fail("gt_storage_attach_areas: regions must be 16-byte aligned, overflow lists 8-byte aligned");
+        regions[q] = static_cast<uint32_t*>(region_of_rank[q]);
+        lists[q] = static_cast<unsigned long long*>(ovf_of_rank[q]);
     }
-    return attach_producer_areas(st, which, "gt_storage_attach_staged", regions.data(), lists.data(), own_inbox, fill_send, fill_recv,
+    return attach_producer_areas(st, which, "gt_storage_attach_areas", regions.data(), lists.data(), own_inbox, fill_send, fill_recv,
                                  true);
+}
+extern "C" int gt_storage_attach_staged(gt_storage* st, int which, void* own_inbox, void* const* stage_of_rank, void* fill_send,
+                                         void* fill_recv) {
+    if (!st || !st->pend || st->world < 2) return fail("gt_storage_attach_staged: not a sharded storage");
+    if (!stage_of_rank) return fail("gt_storage_attach_staged: NULL buffer");
+    const PlanHost& H = st->pend->host;
+    const int W = st->world, me = st->rank;
+    std::vector<void*> regions(W, nullptr), lists(W, nullptr);
+    for (int q = 0; q < W; ++q) {
+        if (q == me) continue;
+        if (!stage_of_rank[q]) return fail("gt_storage_attach_staged: staging area for rank %d is NULL", q);
+        regions[q] = stage_of_rank[q];
+        lists[q] = static_cast<char*>(stage_of_rank[q]) + (inbox_region_entries(H, q) * 4 + 15) / 16 * 16;
+    }
+    return gt_storage_attach_areas(st, which, own_inbox, regions.data(), lists.data(), fill_send, fill_recv);
 }
 
 // Device-to-device copy on a stream of the caller (both pointers valid in this process: local memory or a peer's

@@ -232,6 +232,8 @@ class ShardedStorage:
         self._pending = None           # ce transport: (set, copies-landed events) of the round still to be finished
         self._inbox_ptrs, self._stage = [], []
         self.shipped_bytes = 0         # ce transport: bytes handed to the copy engines (whole regions + overflow lists)
+        self._copy_prof = [] if os.environ.get("GT_SHARD_PROFILE_COPIES", "0") == "1" else None
+        self._peers_applied = [None, None]  # ce transport: event per set, see _finish_fills_and_apply
         W, me = self.world, self.rank
         if self.transport == "nccl":
             self.sets = [ShardExchange(plan, me, torch, dev, group) for _ in range(2)]
@@ -248,6 +250,11 @@ class ShardedStorage:
             self._fill_out = [plan.n_owned[me] + 1] * W
             self._n_fill = plan.nb + W
             self.fill_send, self.fill_recv, self._fx = [], [], []
+            if self.transport == "ce":
+                lay = plan.peer_layout()
+                self._R = [int(x) for x in lay["region"]]
+                self._ovf_off = [int(x) for x in lay["ovf_offset_bytes"]]
+                self._ovf_bytes = [(int(lay["inbox_bytes"][q]) - self._ovf_off[q]) // W for q in range(W)]
             for w in range(2):
                 own = L.gt_peer_alloc(int(L.gt_storage_inbox_bytes(self._h, me)))
                 if not own:
@@ -276,7 +283,9 @@ class ShardedStorage:
                 self.fill_recv.append(fr)
                 self._fx.append(torch.zeros(self._n_fill, dtype=torch.int32, device=dev))
                 if self.transport == "ce":
-                    # local staging area per foreign owner; the copy engines ship it (exchange_and_apply)
+                    # local staging area per foreign owner; the copy engines ship it (exchange_and_apply).  (Mixing in direct
+                    # NVLink stores from k_bucket for some of the peers -- gt_storage_attach_areas allows it -- was measured at
+                    # 8 ranks and lost: three direct peers slow k_bucket from 2.3 to 5.8 ms per round, 158 vs 226 G k-mers/s.)
                     areas = [None if q == me else torch.zeros(int(L.gt_storage_stage_bytes(self._h, q)), dtype=torch.uint8, device=dev)
                              for q in range(W)]
                     sp = (C.c_void_p * W)()
@@ -290,12 +299,10 @@ class ShardedStorage:
                     _capi.check(L.gt_storage_attach_peers(self._h, w, ptrs, fs.data_ptr(), fr.data_ptr()),
                                 "gt_storage_attach_peers")
             if self.transport == "ce":
-                lay = plan.peer_layout()
-                self._R = [int(x) for x in lay["region"]]
-                self._ovf_off = [int(x) for x in lay["ovf_offset_bytes"]]
-                self._ovf_bytes = [(int(lay["inbox_bytes"][q]) - self._ovf_off[q]) // W for q in range(W)]
                 n_cs = max(1, min(int(os.environ.get("GT_SHARD_COPY_STREAMS", "4")), W - 1))
                 self.copy_streams = [torch.cuda.Stream() for _ in range(n_cs)]
+                self.signal_stream = torch.cuda.Stream()
+                self._signal_buf = torch.zeros(1, dtype=torch.int32, device=dev)
             torch.cuda.synchronize()
             dist.barrier(group=group)  # every rank has mapped every inbox before anyone stores into one
 
@@ -378,21 +385,33 @@ class ShardedStorage:
             if self._applied[w ^ 1] is not None:
                 self.stream.wait_event(self._applied[w ^ 1])
             torch.index_select(self.fill_send[w], 0, self._perm, out=self._fx[w])
-            # software NVLink counter: entries this rank produced for peers' slices this round (cursors of foreign
-            # buckets, 16-byte run padding included); nvidia-smi's link counters are not available on every box
-            if getattr(self, "_foreign", None) is None:
-                own = torch.as_tensor(np.asarray(plan.owner) != self.rank, device=self.device)
-                self._foreign = own.to(torch.int64)
-                self._peer_entries = torch.zeros(1, dtype=torch.int64, device=self.device)
-            self._peer_entries += (self.fill_send[w][:plan.nb].to(torch.int64) * self._foreign).sum()
             dist.all_to_all_single(self.fill_recv[w], self._fx[w], self._fill_out, self._fill_in, group=self.group)
             ev = torch.cuda.Event()
             ev.record(self.stream)
+            # software NVLink counter: entries this rank produced for peers' slices this round (cursors of foreign
+            # buckets, 16-byte run padding included); nvidia-smi's link counters are not available on every box.
+            # Read from the gathered copy, after the exchange: the apply below clears fill_send, and the exchange is
+            # what the peers wait for.
+            if getattr(self, "_foreign", None) is None:
+                own = torch.as_tensor((np.asarray(plan.owner) != self.rank)[plan.fill_perm()[plan.fill_perm() < plan.nb]], device=self.device)
+                self._foreign = own.to(torch.int64)
+                self._is_bucket = torch.as_tensor(plan.fill_perm() < plan.nb, device=self.device)
+                self._peer_entries = torch.zeros(1, dtype=torch.int64, device=self.device)
+            self._peer_entries += (self._fx[w][self._is_bucket].to(torch.int64) * self._foreign).sum()
         self.apply_stream.wait_event(ev)
         _capi.check(_capi.lib().gt_storage_apply_store(self._h, w), "gt_storage_apply_store")
         done = torch.cuda.Event()
         done.record(self.apply_stream)
         self._applied[w] = done
+        if self.transport == "ce":
+            # "every rank has applied set w": what the NEXT copies into that set (two rounds on) have to wait for.  A tiny
+            # all-reduce on its own stream, ordered after this rank's apply; it completes here once every rank has entered it.
+            with torch.cuda.stream(self.signal_stream):
+                self.signal_stream.wait_event(done)
+                dist.all_reduce(self._signal_buf, op=dist.ReduceOp.MAX, group=self.group)
+                sig = torch.cuda.Event()
+                sig.record(self.signal_stream)
+            self._peers_applied[w] = sig
 
     def _finish_pending(self):
         if self._pending is None:
@@ -404,17 +423,25 @@ class ShardedStorage:
         self._finish_fills_and_apply(w)
 
     def _ship_and_finish_previous(self):
-        """ce transport, round r (set w): finish round r-1 (its copies have had k_bucket of round r to land), then hand
-        round r's staging areas to the copy engines.  The copies start after the all-to-all of round r-1 has completed
-        here -- every peer has then entered it, i.e. is past its apply of round r-2, the last reader of the inbox set
-        these copies write -- and after k_bucket of round r (both by stream order: one event on the compute stream)."""
+        """ce transport, round r (set w): hand round r's staging areas to the copy engines, then finish round r-1 (its
+        copies have had k_bucket of round r to land).  The copies wait for k_bucket of round r (an event on the compute
+        stream) and for the signal that every rank has applied round r-2, the last reader of the inbox set they write
+        (_finish_fills_and_apply) -- not for the exchange of round r-1, so the copy engines run the rounds back to back:
+        they are what bounds the exchange from 4 ranks up (~420-500 GB/s under load against 745 GB/s idle,
+        scripts/nvlink_probe.py)."""
         torch, L, w, me, W = self.torch, _capi.lib(), self.cur, self.rank, self.world
-        self._finish_pending()
         go = torch.cuda.Event()
-        go.record(self.stream)
+        go.record(self.stream)  # k_bucket of this round has filled the staging areas
         landed = []
         for cs in self.copy_streams:
             cs.wait_event(go)
+            if self._peers_applied[w] is not None:
+                cs.wait_event(self._peers_applied[w])  # every peer is past its last apply of the inbox set these copies write
+        prof = self._copy_prof is not None
+        if prof:  # GT_SHARD_PROFILE_COPIES=1: time every round's copies (first copy stream started -> last copy landed)
+            t0 = torch.cuda.Event(enable_timing=True)
+            t0.record(self.copy_streams[0])
+        n_bytes = 0
         for i in range(1, W):
             q = (me + i) % W  # every rank starts with a different destination
             cs = self.copy_streams[(i - 1) % len(self.copy_streams)]
@@ -424,13 +451,30 @@ class ShardedStorage:
             _capi.check(L.gt_peer_copy_async(dst + me * reg, src, reg, cs.cuda_stream), "gt_peer_copy_async")
             _capi.check(L.gt_peer_copy_async(dst + self._ovf_off[q] + me * self._ovf_bytes[q], src + (reg + 15) // 16 * 16,
                                              self._ovf_bytes[q], cs.cuda_stream), "gt_peer_copy_async")
-            self.shipped_bytes += reg + self._ovf_bytes[q]
+            n_bytes += reg + self._ovf_bytes[q]
+        self.shipped_bytes += n_bytes
         for cs in self.copy_streams:
-            ev = torch.cuda.Event()
+            ev = torch.cuda.Event(enable_timing=prof)
             ev.record(cs)
             landed.append(ev)
+        if prof:
+            self._copy_prof.append((t0, landed, n_bytes))
+        self._finish_pending()  # round r-1: fill exchange (after ITS copies have landed) + apply, queued behind the above
         self._pending = (w, landed)
         self.cur = w ^ 1
+
+    def copy_profile(self, reset=True):
+        """ce transport with GT_SHARD_PROFILE_COPIES=1: (rounds, mean ms per round of copies, GB/s while copying) since the
+        last reset.  Synchronises (collective)."""
+        if not self._copy_prof:
+            return None
+        self.synchronize()
+        ms = [max(t0.elapsed_time(e) for e in landed) for t0, landed, _ in self._copy_prof]
+        nb = sum(b for _, _, b in self._copy_prof)
+        out = {"rounds": len(ms), "ms_per_round": sum(ms) / len(ms), "GBps_while_copying": nb / (sum(ms) / 1e3) / 1e9 if sum(ms) > 0 else None}
+        if reset:
+            self._copy_prof = []
+        return out
 
     def peer_store_bytes(self, reset=False):
         """Bytes this rank's k_bucket stored straight into peers' HBM over NVLink since the last reset (p2p transport;

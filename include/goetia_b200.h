@@ -347,6 +347,13 @@ int gt_storage_attach_peers(gt_storage* st, int which, void* const* inbox_of_ran
 uint64_t gt_storage_stage_bytes(const gt_storage* st, int rank);
 int gt_storage_attach_staged(gt_storage* st, int which, void* own_inbox, void* const* stage_of_rank, void* fill_send,
                              void* fill_recv);
+/* The general form: per foreign owner q, where k_bucket writes this rank's entries (region_of_rank[q]: R_q entries,
+ * 16-byte aligned) and overflow records (ovf_of_rank[q]: GT_OVF_RECORDS records) for q -- a local staging area the
+ * caller ships, or the final place in q's inbox mapped with gt_peer_open (then the stores cross NVLink inside k_bucket,
+ * as with gt_storage_attach_peers).  goetia_b200/shard.py mixes the two per peer so that the SMs' stores and the copy
+ * engines share the NVLink load.  Entry `rank` of both arrays is ignored. */
+int gt_storage_attach_areas(gt_storage* st, int which, void* own_inbox, void* const* region_of_rank,
+                            void* const* ovf_of_rank, void* fill_send, void* fill_recv);
 /* cudaMemcpyAsync(dst, src, bytes) on `stream` (a cudaStream_t); dst / src: local device memory or a peer's
  * allocation mapped with gt_peer_open. */
 int gt_peer_copy_async(void* dst, const void* src, uint64_t bytes, void* stream);
