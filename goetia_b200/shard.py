@@ -233,7 +233,6 @@ class ShardedStorage:
         self._inbox_ptrs, self._stage = [], []
         self.shipped_bytes = 0         # ce transport: bytes handed to the copy engines (whole regions + overflow lists)
         self._copy_prof = [] if os.environ.get("GT_SHARD_PROFILE_COPIES", "0") == "1" else None
-        self._peers_applied = [None, None]  # ce transport: event per set, see _finish_fills_and_apply
         W, me = self.world, self.rank
         if self.transport == "nccl":
             self.sets = [ShardExchange(plan, me, torch, dev, group) for _ in range(2)]
@@ -301,8 +300,6 @@ class ShardedStorage:
             if self.transport == "ce":
                 n_cs = max(1, min(int(os.environ.get("GT_SHARD_COPY_STREAMS", "4")), W - 1))
                 self.copy_streams = [torch.cuda.Stream() for _ in range(n_cs)]
-                self.signal_stream = torch.cuda.Stream()
-                self._signal_buf = torch.zeros(1, dtype=torch.int32, device=dev)
             torch.cuda.synchronize()
             dist.barrier(group=group)  # every rank has mapped every inbox before anyone stores into one
 
@@ -403,15 +400,6 @@ class ShardedStorage:
         done = torch.cuda.Event()
         done.record(self.apply_stream)
         self._applied[w] = done
-        if self.transport == "ce":
-            # "every rank has applied set w": what the NEXT copies into that set (two rounds on) have to wait for.  A tiny
-            # all-reduce on its own stream, ordered after this rank's apply; it completes here once every rank has entered it.
-            with torch.cuda.stream(self.signal_stream):
-                self.signal_stream.wait_event(done)
-                dist.all_reduce(self._signal_buf, op=dist.ReduceOp.MAX, group=self.group)
-                sig = torch.cuda.Event()
-                sig.record(self.signal_stream)
-            self._peers_applied[w] = sig
 
     def _finish_pending(self):
         if self._pending is None:
@@ -423,20 +411,20 @@ class ShardedStorage:
         self._finish_fills_and_apply(w)
 
     def _ship_and_finish_previous(self):
-        """ce transport, round r (set w): hand round r's staging areas to the copy engines, then finish round r-1 (its
-        copies have had k_bucket of round r to land).  The copies wait for k_bucket of round r (an event on the compute
-        stream) and for the signal that every rank has applied round r-2, the last reader of the inbox set they write
-        (_finish_fills_and_apply) -- not for the exchange of round r-1, so the copy engines run the rounds back to back:
-        they are what bounds the exchange from 4 ranks up (~420-500 GB/s under load against 745 GB/s idle,
-        scripts/nvlink_probe.py)."""
+        """ce transport, round r (set w): finish round r-1 (its copies have had k_bucket of round r to land), then hand
+        round r's staging areas to the copy engines.  The copies start after the all-to-all of round r-1 has completed
+        here -- every peer has then entered it, i.e. is past its apply of round r-2, the last reader of the inbox set
+        these copies write -- and after k_bucket of round r (both by stream order: one event on the compute stream).
+        (Letting the copies start earlier, on a separate "every rank has applied" all-reduce issued from a side stream,
+        was measured at 8 ranks and lost, 172 vs 226 G k-mers/s: a collective that is not stream-ordered between two
+        kernels has to wait for a CTA slot beside the SM-filling kernels on every rank.)"""
         torch, L, w, me, W = self.torch, _capi.lib(), self.cur, self.rank, self.world
+        self._finish_pending()
         go = torch.cuda.Event()
-        go.record(self.stream)  # k_bucket of this round has filled the staging areas
+        go.record(self.stream)
         landed = []
         for cs in self.copy_streams:
             cs.wait_event(go)
-            if self._peers_applied[w] is not None:
-                cs.wait_event(self._peers_applied[w])  # every peer is past its last apply of the inbox set these copies write
         prof = self._copy_prof is not None
         if prof:  # GT_SHARD_PROFILE_COPIES=1: time every round's copies (first copy stream started -> last copy landed)
             t0 = torch.cuda.Event(enable_timing=True)
@@ -459,7 +447,6 @@ class ShardedStorage:
             landed.append(ev)
         if prof:
             self._copy_prof.append((t0, landed, n_bytes))
-        self._finish_pending()  # round r-1: fill exchange (after ITS copies have landed) + apply, queued behind the above
         self._pending = (w, landed)
         self.cur = w ^ 1
 

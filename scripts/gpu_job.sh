@@ -1,16 +1,9 @@
 set -x
-R="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
-timeout 400 python -m pytest tests/test_shard.py -m gpu -x -q -k "ce or p2p" > gpurun_out/w_pytest_n2.log 2>&1; echo "rc=$?"
-tail -6 gpurun_out/w_pytest_n2.log
-GT_SHARD_PROFILE_COPIES=1 timeout 300 $R --master-port 29541 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/w_n2.json 2> gpurun_out/w_n2.err; echo "rc=$?"
+timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/y_pytest_all.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/y_pytest_all.log
+timeout 100 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/y_smoke.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/y_smoke.log
+timeout 300 python bench.py > gpurun_out/y_bench_default.json 2> gpurun_out/y_bench_default.err; echo "rc=$?"
 python - <<'PY'
 import json
-for f in ("w_n2",):
-    try:
-        d=json.loads(open("gpurun_out/%s.json"%f).read().strip().splitlines()[-1])
-        print(f, round(d["value"]/1e9,2), d["ms_per_step"], d["config"]["rounds_per_step"], (d.get("e2e") or {}).get("value"), d["check"].get("tables_checksum_equal_reference"), d["check"].get("e2e_tables_checksum_equal_reference"), d["nvlink"].get("copy_engine_profile_rank0"))
-        print("   ", {k:(round(v["ms_total"],1),v["launches"]) for k,v in d["roofline"]["kernels"].items()})
-        print("   ", {k:v for k,v in d["nvlink"].items() if "GBps" in k or "per_kmer" in k})
-    except Exception as e: print(f,"ERR",e)
+d=json.loads(open("gpurun_out/y_bench_default.json").read().strip().splitlines()[-1])
+print(round(d["value"]/1e9,2), round(d["ms_per_step"],2), d["steps"], d["warmup"], (d.get("e2e") or {}).get("value"), d["check"], d["cpu_baseline"]["value"], d["roofline"]["frac"], d["roofline"].get("dram_frac"), d["gpu_launches"])
 PY
-grep -v "^\*\|OMP\|^$" gpurun_out/w_n2.err | tail -5
