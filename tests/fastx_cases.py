@@ -81,3 +81,29 @@ def write_case(dirname, name, data, gz=False):
         with open(fn, "wb") as f:
             f.write(data)
     return fn
+
+
+def bgzf_bytes(data, block=0xff00, level=1, eof_marker=True):
+    """`data` as a BGZF stream (the bgzip / htslib container): gzip members of <= 64 KiB whose extra field 'BC' holds
+    the member's size - 1, closed by the empty end-of-file block.  zlib's gzread -- and so the reference parser --
+    reads it as one ordinary multi-member gzip stream."""
+    import struct
+    import zlib
+    out = []
+    chunks = [data[i:i + block] for i in range(0, len(data), block)] + ([b""] if eof_marker else [])
+    for c in chunks:
+        z = zlib.compressobj(level, zlib.DEFLATED, -15)
+        comp = z.compress(c) + z.flush()
+        bsize = 12 + 6 + len(comp) + 8 - 1
+        assert bsize < 65536
+        out.append(b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize) +
+                   comp + struct.pack("<II", zlib.crc32(c) & 0xffffffff, len(c) & 0xffffffff))
+    return b"".join(out)
+
+
+def write_bgzf_case(dirname, name, data, block=0xff00):
+    fn = os.path.join(dirname, name + ".gz")
+    with open(fn, "wb") as f:
+        f.write(bgzf_bytes(data, block))
+    return fn
+

@@ -86,6 +86,86 @@ def test_parser_matches_reference(tmp_path, case, gz, engine):
         assert seqs3 == seqs and stats3 == stats
 
 
+@pytest.mark.parametrize("block", [0xff00, 700])
+@pytest.mark.parametrize("case", [c for c in cases()], ids=lambda c: c[0])
+def test_bgzf_input_matches_reference(tmp_path, case, block, monkeypatch):
+    """bgzip-compressed input: the blocks are inflated in parallel (fx::Bgzf) and the parser must see the bytes zlib's
+    gzread hands the reference, so every case gives the reference's golden records (full-size and 700-byte blocks:
+    thousands of blocks per ring block, records and lines cut by block boundaries everywhere)."""
+    from goetia_b200 import parsing
+    from tests.fastx_cases import write_bgzf_case
+    monkeypatch.setenv("GT_FASTX_THREADS", "4")
+    name, data, min_length, strict = case
+    fn = write_bgzf_case(str(tmp_path), name, data, block)
+    want = GOLD[os.path.basename(fn)]
+    if "error" in want:
+        exc = parsing.InvalidCharacterException if strict else parsing.InvalidRead
+        with pytest.raises(exc):
+            parse_all(fn, strict, min_length, max_bases=8 << 20)
+        return
+    seqs, stats = parse_all(fn, strict, min_length, max_bases=8 << 20)
+    check(seqs, stats, want)
+    seqs2, stats2 = parse_all(fn, strict, min_length, max_bases=8 << 20, by_record=want["n_reads"] < 5000)
+    assert seqs2 == seqs and stats2 == stats
+
+
+def test_bgzf_mixed_truncated_and_corrupt_streams(tmp_path, monkeypatch):
+    """Where a file stops being well-formed BGZF the reader carries on as zlib's gzread would: a plain gzip member
+    appended to BGZF blocks is read, trailing garbage is ignored, a truncated block ends the input after what could be
+    inflated, a block with a wrong CRC is a read error.  Compared with the compiled reference parser where it is built."""
+    import gzip
+    import zlib
+    from goetia_b200 import parsing
+    from tests.fastx_cases import bgzf_bytes
+    monkeypatch.setenv("GT_FASTX_THREADS", "4")
+    rng = np.random.default_rng(5)
+
+    def fasta(n, tag):
+        return b"".join(b">%s%d\n%s\n" % (tag, i, bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(40, 200))).astype(np.uint8)))
+                        for i in range(n))
+
+    a, b = fasta(3000, b"a"), fasta(500, b"b")
+    files = {
+        "mixed.gz": bgzf_bytes(a, eof_marker=False) + gzip.compress(b, 1) + bgzf_bytes(a[:5000]),
+        "garbage_tail.gz": bgzf_bytes(a) + b"this is not gzip",
+        "truncated.gz": bgzf_bytes(a)[:-3000],
+        "plain_member_first.gz": gzip.compress(b, 1) + bgzf_bytes(a),
+    }
+    want_text = {"mixed.gz": a + b + a[:5000], "garbage_tail.gz": a, "plain_member_first.gz": b + a}
+    try:
+        from oracle import binding
+        Ref = binding.Ref if binding.have_ref() else None
+    except Exception:
+        Ref = None
+    for name, blob in files.items():
+        fn = os.path.join(str(tmp_path), name)
+        with open(fn, "wb") as f:
+            f.write(blob)
+        seqs, stats = parse_all(fn, False, 0, max_bases=8 << 20)
+        if name in want_text:
+            plain = os.path.join(str(tmp_path), name + ".txt")
+            with open(plain, "wb") as f:
+                f.write(want_text[name])
+            seqs_p, stats_p = parse_all(plain, False, 0, max_bases=8 << 20)
+            assert seqs == seqs_p and stats == stats_p, name
+        else:  # truncated: a prefix of the records, the last one possibly cut short
+            full = [ln for ln in a.split(b"\n") if ln and not ln.startswith(b">")]
+            assert 0 < len(seqs) < len(full), name
+            assert seqs[:-1] == full[:len(seqs) - 1] and full[len(seqs) - 1].startswith(seqs[-1]), name
+        if Ref is not None:
+            bb, oo, sk = Ref.parse_file(fn, strict=False, min_length=0)
+            ref_seqs = [bb[int(oo[i]):int(oo[i + 1])].tobytes() for i in range(oo.size - 1)]
+            assert seqs == ref_seqs and stats[1] == sk, name
+    # a corrupted block: CRC mismatch -> the reference's "Error reading stream"
+    blob = bytearray(bgzf_bytes(a))
+    blob[len(blob) // 2] ^= 0x55
+    fn = os.path.join(str(tmp_path), "corrupt.gz")
+    with open(fn, "wb") as f:
+        f.write(bytes(blob))
+    with pytest.raises(parsing.GoetiaFileException):
+        parse_all(fn, False, 0, max_bases=8 << 20)
+
+
 def unpack_batch(words, offsets, flags):
     """The records of a packed batch as text (entries flagged READ_INVALID are alignment gaps, not records)."""
     n = int(offsets[-1])
