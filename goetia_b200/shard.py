@@ -382,19 +382,17 @@ class ShardedStorage:
             if self._applied[w ^ 1] is not None:
                 self.stream.wait_event(self._applied[w ^ 1])
             torch.index_select(self.fill_send[w], 0, self._perm, out=self._fx[w])
+            # software NVLink counter: entries this rank produced for peers' slices this round (cursors of foreign
+            # buckets, 16-byte run padding included); nvidia-smi's link counters are not available on every box.
+            # (Plain elementwise ops only: nothing here may make the host wait for the stream.)
+            if getattr(self, "_foreign", None) is None:
+                own = torch.as_tensor(np.asarray(plan.owner) != self.rank, device=self.device)
+                self._foreign = own.to(torch.int64)
+                self._peer_entries = torch.zeros(1, dtype=torch.int64, device=self.device)
+            self._peer_entries += (self.fill_send[w][:plan.nb].to(torch.int64) * self._foreign).sum()
             dist.all_to_all_single(self.fill_recv[w], self._fx[w], self._fill_out, self._fill_in, group=self.group)
             ev = torch.cuda.Event()
             ev.record(self.stream)
-            # software NVLink counter: entries this rank produced for peers' slices this round (cursors of foreign
-            # buckets, 16-byte run padding included); nvidia-smi's link counters are not available on every box.
-            # Read from the gathered copy, after the exchange: the apply below clears fill_send, and the exchange is
-            # what the peers wait for.
-            if getattr(self, "_foreign", None) is None:
-                own = torch.as_tensor((np.asarray(plan.owner) != self.rank)[plan.fill_perm()[plan.fill_perm() < plan.nb]], device=self.device)
-                self._foreign = own.to(torch.int64)
-                self._is_bucket = torch.as_tensor(plan.fill_perm() < plan.nb, device=self.device)
-                self._peer_entries = torch.zeros(1, dtype=torch.int64, device=self.device)
-            self._peer_entries += (self._fx[w][self._is_bucket].to(torch.int64) * self._foreign).sum()
         self.apply_stream.wait_event(ev)
         _capi.check(_capi.lib().gt_storage_apply_store(self._h, w), "gt_storage_apply_store")
         done = torch.cuda.Event()
@@ -416,8 +414,10 @@ class ShardedStorage:
         here -- every peer has then entered it, i.e. is past its apply of round r-2, the last reader of the inbox set
         these copies write -- and after k_bucket of round r (both by stream order: one event on the compute stream).
         (Letting the copies start earlier, on a separate "every rank has applied" all-reduce issued from a side stream,
-        was measured at 8 ranks and lost, 172 vs 226 G k-mers/s: a collective that is not stream-ordered between two
-        kernels has to wait for a CTA slot beside the SM-filling kernels on every rank.)"""
+        was tried at 8 ranks and measured 172 vs 226 G k-mers/s.  A collective that is not stream-ordered between two
+        kernels has to wait for a CTA slot beside the SM-filling kernels on every rank; the measured build also made the
+        host wait once per round (a boolean-mask index in the byte counter), so the comparison is not clean -- the
+        variant is not in the tree, the validated order is.)"""
         torch, L, w, me, W = self.torch, _capi.lib(), self.cur, self.rank, self.world
         self._finish_pending()
         go = torch.cuda.Event()
