@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- k-mers inserted per second on the BASELINE.json workload (one JSON line).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c3|c1|c2|c4|c5|storage]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c3|c1|c2|c2q|c4|c5|storage]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one pass of the hot path (2-bit pack -> canonical rolling hash -> insert into the
@@ -9,17 +9,27 @@ probabilistic tables) over the whole synthetic read set of the workload.  The de
 is BASELINE.json configs[2] -- the one the metric's target ("BitStorage K=31 insert") and its
 1/2/4/8-GPU scaling are quoted on, and it fits one B200: dBG<BitStorage, CanLemireShifter>,
 K=31, 4 tables x ~8e9 bits (get_n_primes_near_x(4, 8e9)), 50 M synthetic 150 bp reads
-(6.0e9 k-mers per step).
+(6.0e9 k-mers per step) from a counter-based generator, so the CPU reference, one GPU and every
+rank of N see the same read set.
 
   value : device-timed (CUDA events on the library's compute stream), reads resident in HBM as
           ASCII + offsets when the timed region starts.
-  e2e   : the same step through the host-buffer C-ABI call (gt_insert_sequences on pinned host
-          ASCII, H2D copies inside the timed region, k-mer count read back), wall clock.
+  e2e   : the same step through the host-buffer C-ABI call on the parser's product, pinned 2-bit
+          packed reads (gt_insert_sequences_packed; N > 1: ShardedStorage), H2D copies inside the
+          timed region, k-mer count read back, wall clock; e2e_ascii: gt_insert_sequences on
+          pinned ASCII.
+  check : the tables' checksums and occupancy against those of the compiled reference over the
+          same reads (tests/golden/fullsize_golden.json), after the timed and after the e2e steps.
   roofline      : algorithmic 256 B/k-mer (4 x (32 B sector read + 32 B write-back), SURVEY.md
-                  section 8d) over the summed device time of the two insert kernels.
+                  section 8d) over the whole timed region; per-kernel event times, measured DRAM
+                  traffic (profiles/traffic.json), dram_frac and the random-sector rate probed in
+                  the run ride along.
   cpu_baseline  : the unmodified reference (oracle/_ref, compiled from /root/reference) -- or
                   the plain-C port when that .so is absent -- on the box's host cores over a
                   bounded sample of the same reads.
+  N > 1 : reads sharded over the ranks, tables partitioned by slot range, foreign buckets staged
+          locally and shipped by the copy engines over NVLink (goetia_b200/shard.py, transport
+          "ce"; GT_SHARD_TRANSPORT=p2p|nccl select the others).
 
 --impl reference times that CPU implementation as its own arm (rank 0 only).
 The oracle is only ever the checker / the CPU baseline here, never the measured product path.
